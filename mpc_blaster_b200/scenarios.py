@@ -1,0 +1,75 @@
+"""Seeded synthetic workloads for BASELINE.json's configs.
+
+All inputs are generated on the host in FP64 with ``numpy.random.default_rng(seed)``
+so the CPU baseline and the GPU path see bit-identical inputs.  Every x0 lies inside
+the reference's state bounds (simulation_blaster.py:28-29).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NX_FULL, NU_FULL, NP = 17, 6, 25
+
+
+def default_params() -> np.ndarray:
+    """blastermodel.py:280-282: POC Jacobians 0, T_blast = 2.2*9.81."""
+    p = np.zeros(NP)
+    p[24] = 2.2 * 9.81
+    return p
+
+
+def hover_to_setpoint():
+    """Config 1: simulation_blaster.py:47-48."""
+    x0 = np.zeros((1, NX_FULL))
+    yref = np.zeros((1, NX_FULL + NU_FULL))
+    yref[0, 2] = 3.5
+    yref[0, 14] = 0.2
+    return x0, yref
+
+
+def random_setpoints(B: int, seed: int = 1234, nx: int = 17, nu: int = 6):
+    """Configs 2/4/5: randomised x0 inside the bounds and a random position set-point."""
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((B, NX_FULL))
+    x0[:, 0:2] = rng.uniform(-1.0, 1.0, (B, 2))
+    x0[:, 2] = rng.uniform(0.5, 4.0, B)
+    x0[:, 3:5] = rng.uniform(-0.03, 0.03, (B, 2))
+    x0[:, 5] = rng.uniform(-0.30, 0.30, B)
+    x0[:, 6:9] = rng.uniform(-0.3, 0.3, (B, 3))
+    x0[:, 9:12] = rng.uniform(-0.03, 0.03, (B, 3))
+    x0[:, 12] = rng.uniform(0.0, 0.5, B)
+    x0[:, 13] = rng.uniform(-0.3, 0.3, B)
+    yref = np.zeros((B, NX_FULL + NU_FULL))
+    yref[:, 0:2] = rng.uniform(-1.2, 1.2, (B, 2))
+    yref[:, 2] = rng.uniform(0.5, 4.5, B)
+    if nx == NX_FULL:
+        return x0, yref
+    y = np.zeros((B, nx + nu))
+    y[:, :nx] = yref[:, :nx]
+    return np.ascontiguousarray(x0[:, :nx]), y
+
+
+def lemniscate_tracking(B: int, N: int, dt: float = 1.0 / 30, seed: int = 2345, nx: int = 17, nu: int = 6,
+                        amp_xy: float = 1.2, amp_z: float = 1.0, period: float = 2.0):
+    """Config 3: per-stage yref[B, N+1, ny] on a figure-eight with random phase; x0 on the curve."""
+    rng = np.random.default_rng(seed)
+    ph = rng.uniform(0, 2 * np.pi, B)
+    t = np.arange(N + 1) * dt
+    w = 2 * np.pi / period
+    yref = np.zeros((B, N + 1, nx + nu))
+    yref[:, :, 0] = amp_xy * np.sin(w * t[None] + ph[:, None])
+    yref[:, :, 1] = amp_xy * np.sin(2 * w * t[None] + ph[:, None])
+    yref[:, :, 2] = 2.5 + amp_z * np.sin(w * t[None])
+    x0 = np.zeros((B, nx))
+    x0[:, 0:3] = yref[:, 0, 0:3]
+    x0[:, 3:5] = rng.uniform(-0.05, 0.05, (B, 2))
+    x0[:, 6:9] = rng.uniform(-0.3, 0.3, (B, 3))
+    return x0, yref
+
+
+def hover_trim(nu: int = 6, mass: float = 9.0, T_blast: float = 2.2 * 9.81) -> np.ndarray:
+    """Per-rotor thrust that balances gravity with the nozzle pointing down (alpha = 0):
+    sum(T) = M*9.81 - T_blast  (from blastermodel.py:163)."""
+    u = np.zeros(nu)
+    u[:4] = (mass * 9.81 - T_blast) / 4.0
+    return u
