@@ -1,0 +1,128 @@
+/* mpcb.h -- C ABI of the B200-native batched BLASTER MPC solver.
+ *
+ * Drop-in boundary for the per-control-step optimal-control solve of
+ * sml93/mpc_blaster.  In the reference that solve is reached through acados' ctypes
+ * wrapper around a generated shared library; the calls it replaces are the loop body of
+ * reference src/scripts/simulation_blaster.py:56-105:
+ *
+ *   ocp_solver.set(0,'lbx'|'ubx',x)      :60-61   -> x0 argument of mpcb_solve
+ *   ocp_solver.cost_set(k,'yref',yref)   :63-78   -> yref argument (+ yref_mode)
+ *   ocp_solver.set(k,'p',params)         :67-69   -> p argument (+ p_mode)
+ *   ocp_solver.solve()                   :80      -> mpcb_solve
+ *   ocp_solver.get(0,'u') / get(k,'x')   :87-89   -> u0 / X / U outputs
+ *   ocp_solver.get_cost()                :86      -> mpcb_cost
+ *   integrator.set/solve/get             :84-104  -> mpcb_plant_step
+ *   blasterModel(...) ctor + generateController()  (blastermodel.py:16,214-292) -> mpcb_config / mpcb_create
+ *
+ * All array arguments are plain pointers, row-major, FP64.  Unless a function name ends in
+ * _host, pointers are DEVICE pointers on the handle's GPU and the call is asynchronous on
+ * `stream` (a cudaStream_t passed as void*; NULL = default stream).  No allocation happens
+ * inside mpcb_solve / mpcb_plant_step / mpcb_cost, so they are CUDA-graph capturable.
+ * One handle per stream; handles are independent (one per GPU for multi-GPU sharding).
+ *
+ * Return value: 0 on success, negative on API misuse or CUDA failure (message through
+ * mpcb_last_error).  Per-instance solver outcome goes to status[B], mirroring acados'
+ * codes: 0 success, 1 NaN, 2 max-iter, 3 min-step, 4 QP failure.
+ */
+#ifndef MPCB_H
+#define MPCB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB_VARIANT_BLASTER17 17 /* the reference's model: 17 states / 6 inputs / 25 params */
+#define MPCB_VARIANT_QUAD12 12    /* states 0..11, inputs 0..3, gimbal frozen (north_star sizing) */
+#define MPCB_NP 25
+
+/* yref_mode / p_mode */
+#define MPCB_SHARED 0       /* one vector for every instance and stage: yref[ny] / p[25]      */
+#define MPCB_PER_INSTANCE 1 /* yref[B,ny] / p[B,25], same on every stage of an instance      */
+#define MPCB_PER_STAGE 2    /* yref[B,N+1,ny] (terminal row uses its first nx) / p[B,N,25]    */
+
+/* POD mirror of blasterModel(mass,J,l_x,l_y,N,Tf,c,Q,R,Q_t,blastThruster,statesBound,controlBound)
+ * (reference blastermodel.py:16); Q/R/Qt are the diagonals (the reference's weights are
+ * diagonal: acados_ocp_blasterModel.json cost.W). */
+typedef struct mpcb_config {
+    int32_t variant;      /* MPCB_VARIANT_* */
+    int32_t N;            /* horizon length */
+    double dt;            /* Tf / N */
+    double mass, J[9], l_x, l_y, c;
+    double Q[17], R[6], Qt[17];
+    double lbx[17], ubx[17], lbu[6], ubu[6];
+    /* interior-point options (defaults = HPIPM's documented defaults, qp_solver_iter_max from blastermodel.py:279 is 500) */
+    int32_t ipm_max_iter;
+    double ipm_mu0, ipm_thr0;
+    double tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min;
+    int32_t max_batch;    /* capacity of the persistent iterate (instances) */
+    int32_t ws_batch;     /* instances of solver workspace resident at once (0 = auto) */
+    int32_t device;       /* CUDA device ordinal, -1 = current */
+} mpcb_config;
+
+typedef struct mpcb_handle mpcb_handle;
+
+/* canonical constants of reference simulation_blaster.py:12-30, dt = 1/30 s */
+int mpcb_config_default(mpcb_config *cfg, int variant, int N);
+
+int mpcb_create(const mpcb_config *cfg, mpcb_handle **out);
+int mpcb_destroy(mpcb_handle *h);
+const char *mpcb_last_error(const mpcb_handle *h); /* h may be NULL: error of the last failed create */
+
+int mpcb_nx(const mpcb_handle *h);
+int mpcb_nu(const mpcb_handle *h);
+int mpcb_horizon(const mpcb_handle *h);
+
+/* Set the persistent SQP iterate of instances [0,B): X_k = x_init[i] for all k, U_k = u_init
+ * (u_per_instance ? u_init[B,nu] : u_init[nu]).  NULL pointers mean zeros (acados' default
+ * initial iterate).  Replaces ocp_solver.set(k,'x'|'u',...). */
+int mpcb_reset(mpcb_handle *h, const double *x_init, const double *u_init, int u_per_instance, int B, void *stream);
+
+/* One SQP-RTI iteration for instances [0,B): linearise about the stored iterate (RK4 +
+ * forward sensitivities), build the Gauss-Newton QP, solve it, take the full step.
+ * Outputs (each may be NULL): u0[B,nu], X[B,N+1,nx], U[B,N,nu], status[B], iters[B]. */
+int mpcb_solve(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+               double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B, void *stream);
+
+/* Same with HOST buffers: stages inputs through pinned memory, copies to the device,
+ * solves, copies the requested outputs back and synchronises.  p may be NULL (default
+ * parameters: POC Jacobians 0, T_blast = 2.2*9.81, reference blastermodel.py:280-282). */
+int mpcb_solve_host(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+                    double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B);
+
+/* Plant step x+ = RK4(x,u,p) over dt for B instances (AcadosSimSolver of blastermodel.py:290).
+ * p_mode: MPCB_SHARED or MPCB_PER_INSTANCE. */
+int mpcb_plant_step(mpcb_handle *h, const double *x, const double *u, const double *p, int p_mode, double *xnext,
+                    int B, void *stream);
+
+/* `steps` closed-loop control steps entirely on the device (simulation_blaster.py:56-105):
+ * solve from x, apply u0 to the plant, repeat.  x[B,nx] is updated in place.
+ * Optional outputs: u_last[B,nu], n_fail[B] (number of steps whose solve status != 0),
+ * iters_sum[B] (IPM iterations over all steps). */
+int mpcb_closed_loop(mpcb_handle *h, double *x, const double *yref, int yref_mode, const double *p, int p_mode,
+                     int steps, double *u_last, int32_t *n_fail, int32_t *iters_sum, int B, void *stream);
+
+/* cost[B] = sum_k dt/2 |y_k - yref_k|^2_W + 1/2 |x_N - yref_N|^2_We at the stored iterate (get_cost()). */
+int mpcb_cost(mpcb_handle *h, const double *yref, int yref_mode, double *cost, int B, void *stream);
+
+/* Read / write the stored iterate (device pointers; either may be NULL). */
+int mpcb_get_iterate(mpcb_handle *h, double *X, double *U, int B, void *stream);
+int mpcb_set_iterate(mpcb_handle *h, const double *X, const double *U, int B, void *stream);
+
+/* Test hook: run only the rollout + sensitivity kernel for instances [0,B) and return
+ * BAt[B,N,nz,nx] = [B_k'; A_k'] and b[B,N,nx] (device pointers). */
+int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BAt, double *b, int B, void *stream);
+
+/* Number of kernels this library has launched since it was loaded (for bench accounting). */
+int64_t mpcb_kernel_launches(void);
+
+/* Command mapping after the solve (reference mavros_blaster_sim.py:27-30,91-100):
+ * attitude quaternion [w,x,y,z] of R = Rz(psi)Ry(theta)Rx(phi) from x[3:6] and the
+ * normalised collective thrust from the cubic map of thrusterCumul(). quat[B,4], thrust[B]. */
+int mpcb_command_map(mpcb_handle *h, const double *x, const double *u0, double *quat, double *thrust, int B, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB_H */

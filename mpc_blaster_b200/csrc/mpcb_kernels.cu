@@ -1,0 +1,594 @@
+// __global__ wrappers, host batch scheduler and the C ABI (include/mpcb.h) of the
+// B200-native batched BLASTER MPC solver.  Built for sm_100a only; there is no CPU path.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/mpcb.h"
+#include "mpcb_common.cuh"
+#include "mpcb_linearize.cuh"
+#include "mpcb_qp.cuh"
+
+using namespace mpcb;
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+std::string g_create_error;
+
+// ------------------------------------------------------------------ kernels
+__device__ __forceinline__ const double *param_ptr(const double *p, int p_mode, int inst, int k, int N)
+{
+    if (p_mode == MPCB_SHARED) return p;
+    if (p_mode == MPCB_PER_INSTANCE) return p + (size_t)inst * kNP;
+    return p + ((size_t)inst * N + k) * kNP;
+}
+
+// K1: one warp per (instance, shooting interval).
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) linearize_kernel(const __grid_constant__ Params P, const double *__restrict__ X,
+                                                        const double *__restrict__ U, const double *__restrict__ p,
+                                                        int p_mode, double *__restrict__ ws, int inst0, int B)
+{
+    using L = Layout<NX, NU>;
+    const int N = P.N;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= (long long)B * N) return;
+    const int li = (int)(gw / N), k = (int)(gw % N);
+    const int inst = inst0 + li;
+    const double *Xi = X + (size_t)inst * (N + 1) * NX;
+    const double *Ui = U + (size_t)inst * N * NU;
+    double *wsk = ws + (size_t)li * L::instance_stride(N) + (size_t)k * L::STAGE;
+    linearize_warp<NX, NU, double>(P, Xi + (size_t)k * NX, Ui + (size_t)k * NU, Xi + (size_t)(k + 1) * NX,
+                                   param_ptr(p, p_mode, inst, k, N), wsk);
+}
+
+// K2: one warp per instance -- IPM/Riccati QP solve + RTI update.
+template <int NX, int NU, int WPB>
+__global__ void __launch_bounds__(32 * WPB) qp_kernel(const __grid_constant__ Params P, double *__restrict__ X,
+                                                      double *__restrict__ U, const double *__restrict__ x0,
+                                                      const double *__restrict__ yref, int yref_mode,
+                                                      double *__restrict__ ws, double *__restrict__ u0,
+                                                      int32_t *__restrict__ status, int32_t *__restrict__ iters,
+                                                      int inst0, int B)
+{
+    using L = Layout<NX, NU>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QpSmem<NX, NU, double> *sm = reinterpret_cast<QpSmem<NX, NU, double> *>(smem_raw) + (threadIdx.x >> 5);
+    const int N = P.N;
+    const int li = blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (li >= B) return;
+    const int inst = inst0 + li;
+    double *Xi = X + (size_t)inst * (N + 1) * NX;
+    double *Ui = U + (size_t)inst * N * NU;
+    const double *yr = yref;
+    if (yref_mode == MPCB_PER_INSTANCE) yr = yref + (size_t)inst * (NX + NU);
+    if (yref_mode == MPCB_PER_STAGE) yr = yref + (size_t)inst * (N + 1) * (NX + NU);
+    int it = 0;
+    const int st = qp_solve_warp<NX, NU, double>(P, *sm, ws + (size_t)li * L::instance_stride(N), Xi, Ui,
+                                                 x0 + (size_t)inst * NX, yr, yref_mode == MPCB_PER_STAGE, &it);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        if (status) status[inst] = st;
+        if (iters) iters[inst] = it;
+    }
+    __syncwarp();
+    if (u0 && lane < NU) u0[(size_t)inst * NU + lane] = Ui[lane];
+}
+
+template <int NX, int NU>
+__global__ void plant_kernel(const __grid_constant__ Params P, const double *__restrict__ x, const double *__restrict__ u,
+                             const double *__restrict__ p, int p_mode, double *__restrict__ xn, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    plant_step_thread<NX, NU, double>(P, x + (size_t)i * NX, u + (size_t)i * NU,
+                                      p_mode == MPCB_SHARED ? p : p + (size_t)i * kNP, xn + (size_t)i * NX);
+}
+
+template <int NX, int NU>
+__global__ void reset_kernel(const __grid_constant__ Params P, double *__restrict__ X, double *__restrict__ U,
+                             const double *__restrict__ x_init, const double *__restrict__ u_init, int u_per_instance,
+                             int B)
+{
+    const int N = P.N;
+    const size_t per = (size_t)(N + 1) * NX + (size_t)N * NU;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= per * B) return;
+    const int inst = (int)(tid / per);
+    const size_t r = tid % per;
+    if (r < (size_t)(N + 1) * NX) {
+        X[(size_t)inst * (N + 1) * NX + r] = x_init ? x_init[(size_t)inst * NX + r % NX] : 0.0;
+    } else {
+        const size_t q = r - (size_t)(N + 1) * NX;
+        U[(size_t)inst * N * NU + q] = u_init ? u_init[(u_per_instance ? (size_t)inst * NU : 0) + q % NU] : 0.0;
+    }
+}
+
+// get_cost() [upstream D10]
+template <int NX, int NU>
+__global__ void cost_kernel(const __grid_constant__ Params P, const double *__restrict__ X, const double *__restrict__ U,
+                            const double *__restrict__ yref, int yref_mode, double *__restrict__ cost, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int N = P.N, NY = NX + NU;
+    const double *Xi = X + (size_t)i * (N + 1) * NX, *Ui = U + (size_t)i * N * NU;
+    const double *yr = yref;
+    if (yref_mode == MPCB_PER_INSTANCE) yr = yref + (size_t)i * NY;
+    if (yref_mode == MPCB_PER_STAGE) yr = yref + (size_t)i * (N + 1) * NY;
+    double acc = 0.0;
+    for (int k = 0; k <= N; k++) {
+        const double *y = yr + (yref_mode == MPCB_PER_STAGE ? (size_t)k * NY : 0);
+        double s = 0.0;
+        for (int j = 0; j < NX; j++) {
+            const double e = Xi[(size_t)k * NX + j] - y[j];
+            s += (k < N ? P.Q[j] : P.Qt[j]) * e * e;
+        }
+        if (k < N)
+            for (int j = 0; j < NU; j++) {
+                const double e = Ui[(size_t)k * NU + j] - y[NX + j];
+                s += P.R[j] * e * e;
+            }
+        acc += (k < N ? 0.5 * P.dt : 0.5) * s;
+    }
+    cost[i] = acc;
+}
+
+template <int NX, int NU>
+__global__ void debug_copy_kernel(const __grid_constant__ Params P, const double *__restrict__ ws, double *__restrict__ BAt,
+                                  double *__restrict__ b, int inst0, int B)
+{
+    using L = Layout<NX, NU>;
+    const int N = P.N;
+    const size_t per = (size_t)N * (L::NZ * NX + NX);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= per * B) return;
+    const int li = (int)(tid / per);
+    const size_t r = tid % per;
+    const int k = (int)(r / (L::NZ * NX + NX));
+    const int e = (int)(r % (L::NZ * NX + NX));
+    const double *wk = ws + (size_t)li * L::instance_stride(N) + (size_t)k * L::STAGE;
+    const size_t inst = (size_t)inst0 + li;
+    if (e < L::NZ * NX) BAt[(inst * N + k) * (L::NZ * NX) + e] = wk[L::O_BAT + e];
+    else b[(inst * N + k) * NX + (e - L::NZ * NX)] = wk[L::O_B + e - L::NZ * NX];
+}
+
+// closed-loop bookkeeping: x <- xnext, count failures / iterations
+template <int NX>
+__global__ void loop_book_kernel(double *__restrict__ x, const double *__restrict__ xn, const int32_t *__restrict__ status,
+                                 const int32_t *__restrict__ iters, int32_t *__restrict__ n_fail,
+                                 int32_t *__restrict__ iters_sum, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    for (int j = 0; j < NX; j++) x[(size_t)i * NX + j] = xn[(size_t)i * NX + j];
+    if (n_fail && status[i] != 0) n_fail[i] += 1;
+    if (iters_sum) iters_sum[i] += iters[i];
+}
+
+// reference mavros_blaster_sim.py:27-30,91-100
+__global__ void command_map_kernel(const double *__restrict__ x, const double *__restrict__ u0, int nx, int nu,
+                                   double *__restrict__ quat, double *__restrict__ thrust, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    if (quat) euler_to_quat<double>(x[(size_t)i * nx + 3], x[(size_t)i * nx + 4], x[(size_t)i * nx + 5], quat + (size_t)i * 4);
+    if (thrust) {
+        const double *u = u0 + (size_t)i * nu;
+        const double avg = 2.3 * (0.25 * (u[0] + u[1] + u[2] + u[3])) / 9.81;
+        thrust[i] = 0.0014 * avg * avg * avg - 0.0263 * avg * avg + 0.2464 * avg - 0.0286;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ handle
+struct mpcb_handle {
+    mpcb_config cfg;
+    Params P;
+    int nx, nu, N, device;
+    int max_batch, ws_batch;
+    size_t ws_stride;  // doubles per instance
+    double *X = nullptr, *U = nullptr, *ws = nullptr;
+    double *p_default = nullptr;  // device copy of the default parameter vector
+    int32_t *status_scratch = nullptr, *iters_scratch = nullptr;
+    double *xn_scratch = nullptr, *u0_scratch = nullptr;
+    // host staging for mpcb_solve_host
+    double *h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+    double *d_stage = nullptr;
+    size_t d_stage_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+};
+
+namespace {
+
+int fail(mpcb_handle *h, const char *what, cudaError_t e = cudaSuccess)
+{
+    std::string m = what;
+    if (e != cudaSuccess) { m += ": "; m += cudaGetErrorString(e); }
+    if (h) h->err = m; else g_create_error = m;
+    return -1;
+}
+
+#define CK(h, call)                                             \
+    do {                                                        \
+        cudaError_t e_ = (call);                                \
+        if (e_ != cudaSuccess) return fail((h), #call, e_);     \
+    } while (0)
+
+void invert3(const double *J, double *Ji)
+{
+    const double a = J[0], b = J[1], c = J[2], d = J[3], e = J[4], f = J[5], g = J[6], hh = J[7], i = J[8];
+    const double det = a * (e * i - f * hh) - b * (d * i - f * g) + c * (d * hh - e * g);
+    const double r = 1.0 / det;
+    Ji[0] = (e * i - f * hh) * r; Ji[1] = (c * hh - b * i) * r; Ji[2] = (b * f - c * e) * r;
+    Ji[3] = (f * g - d * i) * r;  Ji[4] = (a * i - c * g) * r;  Ji[5] = (c * d - a * f) * r;
+    Ji[6] = (d * hh - e * g) * r; Ji[7] = (b * g - a * hh) * r; Ji[8] = (a * e - b * d) * r;
+}
+
+Params make_params(const mpcb_config &c)
+{
+    Params P;
+    memset(&P, 0, sizeof(P));
+    P.variant = c.variant; P.N = c.N; P.dt = c.dt; P.mass = c.mass; P.inv_mass = 1.0 / c.mass;
+    memcpy(P.J, c.J, sizeof(P.J));
+    invert3(c.J, P.Jinv);
+    P.l_x = c.l_x; P.l_y = c.l_y; P.c = c.c;
+    // moment map, reference blastermodel.py:95-101
+    const double G[3][4] = {{-c.l_y, c.l_y, -c.l_y, c.l_y}, {-c.l_x, c.l_x, c.l_x, -c.l_x}, {-c.c, -c.c, c.c, c.c}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 4; j++) {
+            double a = 0;
+            for (int k = 0; k < 3; k++) a += P.Jinv[3 * i + k] * G[k][j];
+            P.JinvG[4 * i + j] = a;
+        }
+    memcpy(P.Q, c.Q, sizeof(P.Q)); memcpy(P.R, c.R, sizeof(P.R)); memcpy(P.Qt, c.Qt, sizeof(P.Qt));
+    memcpy(P.lbx, c.lbx, sizeof(P.lbx)); memcpy(P.ubx, c.ubx, sizeof(P.ubx));
+    memcpy(P.lbu, c.lbu, sizeof(P.lbu)); memcpy(P.ubu, c.ubu, sizeof(P.ubu));
+    P.ipm_max_iter = c.ipm_max_iter; P.ipm_mu0 = c.ipm_mu0; P.ipm_thr0 = c.ipm_thr0;
+    P.tol_stat = c.tol_stat; P.tol_eq = c.tol_eq; P.tol_ineq = c.tol_ineq; P.tol_comp = c.tol_comp;
+    P.alpha_min = c.alpha_min;
+    return P;
+}
+
+constexpr int kWPB = 1;  // warps (= instances) per CTA of the QP kernel
+
+template <int NX, int NU>
+int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+                        double *u0, int32_t *status, int32_t *iters, int B, cudaStream_t s)
+{
+    const size_t smem = sizeof(QpSmem<NX, NU, double>) * kWPB;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(h, cudaFuncSetAttribute(qp_kernel<NX, NU, kWPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    for (int i0 = 0; i0 < B; i0 += h->ws_batch) {
+        const int nb = (B - i0 < h->ws_batch) ? B - i0 : h->ws_batch;
+        const long long warps = (long long)nb * h->N;
+        const unsigned g1 = (unsigned)((warps * 32 + 127) / 128);
+        linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+        qp_kernel<NX, NU, kWPB><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws,
+                                                                                  u0, status, iters, i0, nb);
+        g_launches += 2;
+    }
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int check_batch(mpcb_handle *h, int B)
+{
+    if (!h) return fail(nullptr, "null handle");
+    if (B < 0 || B > h->max_batch) return fail(h, "batch size exceeds max_batch");
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int mpcb_config_default(mpcb_config *cfg, int variant, int N)
+{
+    if (!cfg || (variant != 17 && variant != 12) || N < 2) return -1;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->variant = variant; cfg->N = N; cfg->dt = 2.0 / 60.0;
+    cfg->mass = 9.0;
+    cfg->J[0] = 0.50781; cfg->J[4] = 0.47314; cfg->J[8] = 0.72975;
+    cfg->l_x = 0.3434; cfg->l_y = 0.3475; cfg->c = 0.03;
+    const double Q[17] = {1e3, 1e3, 1e3, 1e3, 1e3, 1e3, 5, 5, 5, 10, 10, 10, 1e-2, 1e-2, 1e3, 1e3, 1e3};
+    const double R[6] = {5e-2, 5e-2, 5e-2, 5e-2, 1e-5, 1e-5};
+    const double lbx[17] = {-1.5, -1.5, 0, -0.174532925, -0.174532925, -0.349066, -1.0, -1.0, -1.0, -0.0872665, -0.0872665,
+                            -0.0872665, -0.174532925, -0.523599, -1.5, -1.5, -2.5};
+    const double ubx[17] = {1.5, 1.5, 5.0, 0.174532925, 0.174532925, 0.349066, 1.0, 1.0, 1.0, 0.0872665, 0.0872665,
+                            0.0872665, 1.22173, 0.523599, 1.5, 1.5, 2.5};
+    const double lbu[6] = {0, 0, 0, 0, -0.0872665, -0.0872665}, ubu[6] = {65, 65, 65, 65, 0.0872665, 0.0872665};
+    for (int i = 0; i < 17; i++) { cfg->Q[i] = Q[i]; cfg->Qt[i] = 10 * Q[i]; cfg->lbx[i] = lbx[i]; cfg->ubx[i] = ubx[i]; }
+    for (int i = 0; i < 6; i++) { cfg->R[i] = R[i]; cfg->lbu[i] = lbu[i]; cfg->ubu[i] = ubu[i]; }
+    cfg->ipm_max_iter = 60; cfg->ipm_mu0 = 1e4; cfg->ipm_thr0 = 10.0;
+    cfg->tol_stat = 1e-6; cfg->tol_eq = 1e-8; cfg->tol_ineq = 1e-8; cfg->tol_comp = 1e-8; cfg->alpha_min = 1e-8;
+    cfg->max_batch = 1024; cfg->ws_batch = 0; cfg->device = -1;
+    return 0;
+}
+
+int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, "null argument");
+    if (cfg->variant != 17 && cfg->variant != 12) return fail(nullptr, "variant must be 17 or 12");
+    if (cfg->N < 2 || cfg->N > 4096) return fail(nullptr, "horizon out of range");
+    if (cfg->max_batch < 1) return fail(nullptr, "max_batch must be >= 1");
+    if (!(cfg->dt > 0) || !(cfg->mass > 0)) return fail(nullptr, "dt and mass must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, "no CUDA device: this library has no CPU path", e);
+    mpcb_handle *h = new (std::nothrow) mpcb_handle();
+    if (!h) return fail(nullptr, "out of host memory");
+    h->cfg = *cfg;
+    h->P = make_params(*cfg);
+    h->nx = cfg->variant == 17 ? 17 : 12;
+    h->nu = cfg->variant == 17 ? 6 : 4;
+    h->N = cfg->N;
+    h->max_batch = cfg->max_batch;
+    if (cfg->device >= 0) {
+        h->device = cfg->device;
+    } else {
+        cudaGetDevice(&h->device);
+    }
+    e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) { fail(nullptr, "cudaSetDevice", e); delete h; return -1; }
+    h->ws_stride = cfg->variant == 17 ? Layout<17, 6>::instance_stride(h->N) : Layout<12, 4>::instance_stride(h->N);
+    int wsb = cfg->ws_batch;
+    if (wsb <= 0) {
+        // auto: at most ~24 GiB of solver workspace resident at once
+        const size_t budget = (size_t)24 << 30;
+        size_t cap = budget / (h->ws_stride * sizeof(double));
+        if (cap < 1) cap = 1;
+        wsb = (size_t)h->max_batch < cap ? h->max_batch : (int)cap;
+    }
+    if (wsb > h->max_batch) wsb = h->max_batch;
+    h->ws_batch = wsb;
+    const size_t B = (size_t)h->max_batch;
+    const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;
+#define ALLOC(ptr, bytes)                                                                   \
+    do {                                                                                    \
+        e = cudaMalloc((void **)&(ptr), (bytes));                                           \
+        if (e != cudaSuccess) { fail(nullptr, "cudaMalloc " #ptr, e); mpcb_destroy(h); return -1; } \
+    } while (0)
+    ALLOC(h->X, nX * sizeof(double));
+    ALLOC(h->U, nU * sizeof(double));
+    ALLOC(h->ws, (size_t)h->ws_batch * h->ws_stride * sizeof(double));
+    ALLOC(h->p_default, kNP * sizeof(double));
+    ALLOC(h->status_scratch, B * sizeof(int32_t));
+    ALLOC(h->iters_scratch, B * sizeof(int32_t));
+    ALLOC(h->xn_scratch, B * h->nx * sizeof(double));
+    ALLOC(h->u0_scratch, B * h->nu * sizeof(double));
+#undef ALLOC
+    double pd[kNP] = {0};
+    pd[24] = 2.2 * 9.81;  // reference blastermodel.py:280-282
+    cudaMemcpy(h->p_default, pd, sizeof(pd), cudaMemcpyHostToDevice);
+    cudaMemset(h->X, 0, nX * sizeof(double));
+    cudaMemset(h->U, 0, nU * sizeof(double));
+    cudaMemset(h->ws, 0, (size_t)h->ws_batch * h->ws_stride * sizeof(double));
+    e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { fail(nullptr, "cudaStreamCreate", e); mpcb_destroy(h); return -1; }
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { fail(nullptr, "init", e); mpcb_destroy(h); return -1; }
+    *out = h;
+    return 0;
+}
+
+int mpcb_destroy(mpcb_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->X); cudaFree(h->U); cudaFree(h->ws); cudaFree(h->p_default);
+    cudaFree(h->status_scratch); cudaFree(h->iters_scratch); cudaFree(h->xn_scratch); cudaFree(h->u0_scratch);
+    cudaFree(h->d_stage);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+const char *mpcb_last_error(const mpcb_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int mpcb_nx(const mpcb_handle *h) { return h ? h->nx : -1; }
+int mpcb_nu(const mpcb_handle *h) { return h ? h->nu : -1; }
+int mpcb_horizon(const mpcb_handle *h) { return h ? h->N : -1; }
+int64_t mpcb_kernel_launches(void) { return g_launches.load(); }
+
+int mpcb_reset(mpcb_handle *h, const double *x_init, const double *u_init, int u_per_instance, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t per = (size_t)(h->N + 1) * h->nx + (size_t)h->N * h->nu;
+    const unsigned grid = (unsigned)((per * B + 255) / 256);
+    if (h->nx == 17) reset_kernel<17, 6><<<grid, 256, 0, s>>>(h->P, h->X, h->U, x_init, u_init, u_per_instance, B);
+    else reset_kernel<12, 4><<<grid, 256, 0, s>>>(h->P, h->X, h->U, x_init, u_init, u_per_instance, B);
+    g_launches += 1;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_solve(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+               double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (!x0 || !yref) return fail(h, "x0 and yref are required");
+    if (yref_mode < 0 || yref_mode > 2 || p_mode < 0 || p_mode > 2) return fail(h, "bad yref_mode / p_mode");
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!p) { p = h->p_default; p_mode = MPCB_SHARED; }
+    int rc = (h->nx == 17) ? launch_solve_chunks<17, 6>(h, x0, yref, yref_mode, p, p_mode, u0, status, iters, B, s)
+                           : launch_solve_chunks<12, 4>(h, x0, yref, yref_mode, p, p_mode, u0, status, iters, B, s);
+    if (rc) return rc;
+    if (X) CK(h, cudaMemcpyAsync(X, h->X, (size_t)B * (h->N + 1) * h->nx * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (U) CK(h, cudaMemcpyAsync(U, h->U, (size_t)B * h->N * h->nu * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int mpcb_solve_host(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+                    double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B)
+{
+    if (check_batch(h, B)) return -1;
+    if (!x0 || !yref) return fail(h, "x0 and yref are required");
+    if (yref_mode < 0 || yref_mode > 2 || p_mode < 0 || p_mode > 2) return fail(h, "bad yref_mode / p_mode");
+    if (B == 0) return 0;
+    CK(h, cudaSetDevice(h->device));
+    const int nx = h->nx, nu = h->nu, N = h->N, ny = nx + nu;
+    const size_t n_x0 = (size_t)B * nx;
+    const size_t n_y = yref_mode == MPCB_SHARED ? ny : yref_mode == MPCB_PER_INSTANCE ? (size_t)B * ny : (size_t)B * (N + 1) * ny;
+    const size_t n_p = !p ? 0 : p_mode == MPCB_SHARED ? kNP : p_mode == MPCB_PER_INSTANCE ? (size_t)B * kNP : (size_t)B * N * kNP;
+    const size_t n_u0 = u0 ? (size_t)B * nu : 0, n_X = X ? (size_t)B * (N + 1) * nx : 0, n_U = U ? (size_t)B * N * nu : 0;
+    const size_t n_st = (size_t)B;  // int32 status + iters packed behind the doubles
+    const size_t in_d = n_x0 + n_y + n_p;
+    const size_t out_d = n_u0 + n_X + n_U;
+    const size_t bytes = (in_d + out_d) * sizeof(double) + 2 * n_st * sizeof(int32_t);
+    if (bytes > h->h_pin_bytes) {
+        if (h->h_pin) cudaFreeHost(h->h_pin);
+        cudaFree(h->d_stage);
+        h->h_pin = nullptr; h->d_stage = nullptr; h->h_pin_bytes = h->d_stage_bytes = 0;
+        CK(h, cudaMallocHost((void **)&h->h_pin, bytes));
+        CK(h, cudaMalloc((void **)&h->d_stage, bytes));
+        h->h_pin_bytes = h->d_stage_bytes = bytes;
+    }
+    cudaStream_t s = h->own_stream;
+    double *hp = h->h_pin, *dp = h->d_stage;
+    memcpy(hp, x0, n_x0 * sizeof(double));
+    memcpy(hp + n_x0, yref, n_y * sizeof(double));
+    if (p) memcpy(hp + n_x0 + n_y, p, n_p * sizeof(double));
+    CK(h, cudaMemcpyAsync(dp, hp, in_d * sizeof(double), cudaMemcpyHostToDevice, s));
+    double *d_u0 = dp + in_d, *d_X = d_u0 + n_u0, *d_U = d_X + n_X;
+    int32_t *d_st = (int32_t *)(d_U + n_U), *d_it = d_st + n_st;
+    int rc = mpcb_solve(h, dp, dp + n_x0, yref_mode, p ? dp + n_x0 + n_y : nullptr, p_mode, u0 ? d_u0 : nullptr,
+                        X ? d_X : nullptr, U ? d_U : nullptr, d_st, d_it, B, s);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(hp + in_d, dp + in_d, out_d * sizeof(double) + 2 * n_st * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(h, cudaStreamSynchronize(s));
+    if (u0) memcpy(u0, hp + in_d, n_u0 * sizeof(double));
+    if (X) memcpy(X, hp + in_d + n_u0, n_X * sizeof(double));
+    if (U) memcpy(U, hp + in_d + n_u0 + n_X, n_U * sizeof(double));
+    const int32_t *h_st = (const int32_t *)(hp + in_d + out_d);
+    if (status) memcpy(status, h_st, n_st * sizeof(int32_t));
+    if (iters) memcpy(iters, h_st + n_st, n_st * sizeof(int32_t));
+    return 0;
+}
+
+int mpcb_plant_step(mpcb_handle *h, const double *x, const double *u, const double *p, int p_mode, double *xnext,
+                    int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (!x || !u || !xnext) return fail(h, "null argument");
+    if (p_mode != MPCB_SHARED && p_mode != MPCB_PER_INSTANCE) return fail(h, "plant p_mode must be SHARED or PER_INSTANCE");
+    if (B == 0) return 0;
+    if (!p) { p = h->p_default; p_mode = MPCB_SHARED; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (B + 127) / 128;
+    if (h->nx == 17) plant_kernel<17, 6><<<grid, 128, 0, s>>>(h->P, x, u, p, p_mode, xnext, B);
+    else plant_kernel<12, 4><<<grid, 128, 0, s>>>(h->P, x, u, p, p_mode, xnext, B);
+    g_launches += 1;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_closed_loop(mpcb_handle *h, double *x, const double *yref, int yref_mode, const double *p, int p_mode,
+                     int steps, double *u_last, int32_t *n_fail, int32_t *iters_sum, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (!x || !yref || steps < 0) return fail(h, "bad argument");
+    if (p && p_mode == MPCB_PER_STAGE) return fail(h, "closed loop takes p SHARED or PER_INSTANCE");
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_fail) CK(h, cudaMemsetAsync(n_fail, 0, (size_t)B * sizeof(int32_t), s));
+    if (iters_sum) CK(h, cudaMemsetAsync(iters_sum, 0, (size_t)B * sizeof(int32_t), s));
+    double *u0 = u_last ? u_last : h->u0_scratch;
+    for (int t = 0; t < steps; t++) {
+        if (mpcb_solve(h, x, yref, yref_mode, p, p_mode, u0, nullptr, nullptr, h->status_scratch, h->iters_scratch, B, s))
+            return -1;
+        if (mpcb_plant_step(h, x, u0, p, p ? p_mode : MPCB_SHARED, h->xn_scratch, B, s)) return -1;
+        const unsigned grid = (B + 127) / 128;
+        if (h->nx == 17)
+            loop_book_kernel<17><<<grid, 128, 0, s>>>(x, h->xn_scratch, h->status_scratch, h->iters_scratch, n_fail, iters_sum, B);
+        else
+            loop_book_kernel<12><<<grid, 128, 0, s>>>(x, h->xn_scratch, h->status_scratch, h->iters_scratch, n_fail, iters_sum, B);
+        g_launches += 1;
+    }
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_cost(mpcb_handle *h, const double *yref, int yref_mode, double *cost, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (!yref || !cost) return fail(h, "null argument");
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (B + 127) / 128;
+    if (h->nx == 17) cost_kernel<17, 6><<<grid, 128, 0, s>>>(h->P, h->X, h->U, yref, yref_mode, cost, B);
+    else cost_kernel<12, 4><<<grid, 128, 0, s>>>(h->P, h->X, h->U, yref, yref_mode, cost, B);
+    g_launches += 1;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_get_iterate(mpcb_handle *h, double *X, double *U, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (X) CK(h, cudaMemcpyAsync(X, h->X, (size_t)B * (h->N + 1) * h->nx * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (U) CK(h, cudaMemcpyAsync(U, h->U, (size_t)B * h->N * h->nu * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int mpcb_set_iterate(mpcb_handle *h, const double *X, const double *U, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (X) CK(h, cudaMemcpyAsync(h->X, X, (size_t)B * (h->N + 1) * h->nx * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (U) CK(h, cudaMemcpyAsync(h->U, U, (size_t)B * h->N * h->nu * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BAt, double *b, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (!BAt || !b) return fail(h, "null argument");
+    if (!p) { p = h->p_default; p_mode = MPCB_SHARED; }
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < B; i0 += h->ws_batch) {
+        const int nb = (B - i0 < h->ws_batch) ? B - i0 : h->ws_batch;
+        const long long warps = (long long)nb * h->N;
+        const unsigned g1 = (unsigned)((warps * 32 + 127) / 128);
+        if (h->nx == 17) {
+            linearize_kernel<17, 6><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+            const size_t per = (size_t)h->N * (23 * 17 + 17);
+            debug_copy_kernel<17, 6><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, BAt, b, i0, nb);
+        } else {
+            linearize_kernel<12, 4><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+            const size_t per = (size_t)h->N * (16 * 12 + 12);
+            debug_copy_kernel<12, 4><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, BAt, b, i0, nb);
+        }
+        g_launches += 2;
+    }
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_command_map(mpcb_handle *h, const double *x, const double *u0, double *quat, double *thrust, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (!x || (thrust && !u0)) return fail(h, "null argument");
+    if (B == 0) return 0;
+    command_map_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, u0, h->nx, h->nu, quat, thrust, B);
+    g_launches += 1;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

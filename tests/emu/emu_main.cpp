@@ -1,0 +1,60 @@
+// Host build of the warp-synchronous kernel bodies (TEST INFRASTRUCTURE ONLY).
+// Compiles mpc_blaster_b200/csrc/mpcb_linearize.cuh and mpcb_qp.cuh with g++ under
+// -DMPCB_HOST_EMU, where a warp is 32 fibers (warp_emu.h), and exposes a tiny C API so
+// that tests/test_kernel_emulation.py can check the kernel logic against the oracle
+// without a GPU.  Never part of the product library.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "mpcb_common.cuh"
+#include "mpcb_linearize.cuh"
+#include "mpcb_qp.cuh"
+
+using namespace mpcb;
+
+template <int NX, int NU>
+static int rti_one(const Params &P, double *X, double *U, const double *x0, const double *yref, int yps, const double *p,
+                   int p_per_stage, int *iters, double *BAt_out, double *b_out)
+{
+    using L = Layout<NX, NU>;
+    const int N = P.N;
+    std::vector<double> ws(L::instance_stride(N), 0.0);
+    for (int k = 0; k < N; k++) {
+        const double *pk = p + (p_per_stage ? (size_t)k * kNP : 0);
+        emu::run_warp([&]() {
+            linearize_warp<NX, NU, double>(P, X + (size_t)k * NX, U + (size_t)k * NU, X + (size_t)(k + 1) * NX, pk,
+                                           ws.data() + (size_t)k * L::STAGE);
+        });
+        if (BAt_out) memcpy(BAt_out + (size_t)k * L::NZ * NX, ws.data() + (size_t)k * L::STAGE + L::O_BAT, sizeof(double) * L::NZ * NX);
+        if (b_out) memcpy(b_out + (size_t)k * NX, ws.data() + (size_t)k * L::STAGE + L::O_B, sizeof(double) * NX);
+    }
+    int status = -1, it = 0;
+    QpSmem<NX, NU, double> sm;
+    memset(&sm, 0, sizeof(sm));
+    emu::run_warp([&]() {
+        int my_it = 0;
+        int st = qp_solve_warp<NX, NU, double>(P, sm, ws.data(), X, U, x0, yref, yps, &my_it);
+        if (emu::lane() == 0) { status = st; it = my_it; }
+    });
+    *iters = it;
+    return status;
+}
+
+extern "C" {
+
+size_t emu_params_size() { return sizeof(Params); }
+
+int emu_rti_solve(const Params *P, double *X, double *U, const double *x0, const double *yref, int yps, const double *p,
+                  int p_per_stage, int *iters, double *BAt_out, double *b_out)
+{
+    if (P->variant == 17) return rti_one<17, 6>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+    return rti_one<12, 4>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+}
+
+void emu_plant_step(const Params *P, const double *x, const double *u, const double *p, double *xn)
+{
+    if (P->variant == 17) plant_step_thread<17, 6, double>(*P, x, u, p, xn);
+    else plant_step_thread<12, 4, double>(*P, x, u, p, xn);
+}
+}
