@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched BLASTER MPC solves/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): 1,024 independent BLASTER17 instances per GPU,
+horizon N=20, randomised x0 / set-point (mpc_blaster_b200.scenarios.random_setpoints), SQP
+iterate initialised at (x0, hover trim), cold-started QP.  One "step" = one SQP-RTI solve of
+the whole batch (rollout+sensitivities kernel, then the Riccati-IPM kernel).  The iterate is
+re-initialised and L2 is flushed between steps, outside the timed events, so every timed
+step does the same work from a cold cache.  Multi-GPU: one process per GPU, each with its
+own 1,024-instance batch (weak scaling), no collective on the solve path; one final gather.
+
+`value` is timed with CUDA events on the launching stream with inputs resident in HBM;
+`e2e` goes through the C ABI's host entry point (mpcb_solve_host: pinned staging, H2D,
+solve, D2H) with NumPy buffers.  `cpu_baseline` / `--impl reference` time the C oracle
+(oracle/mpc_oracle.c, kind "port": acados/HPIPM cannot be built here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mpc_blaster_b200 import scenarios as sc  # noqa: E402
+
+HORIZON = 20
+BATCH = 1024
+VARIANT = 17
+METRIC = "MPC solves/sec (N=20, batched)"
+UNIT = "solves/s"
+
+
+def workload(rank: int, batch: int = BATCH, variant: int = VARIANT):
+    nx, nu = (17, 6) if variant == 17 else (12, 4)
+    x0, yref = sc.random_setpoints(batch, seed=1234 + rank, nx=nx, nu=nu)
+    return x0, yref, sc.hover_trim(nu)
+
+
+def config_dict(world: int, batch: int, horizon: int, variant: int):
+    return {"workload": f"configs[1]: batch of {batch} independent quadrotor MPC instances per GPU (randomised x0/x_ref), "
+                        f"N={horizon}, BLASTER{variant} ({'17 states / 6 inputs' if variant == 17 else '12 states / 4 inputs'}), "
+                        "one SQP-RTI iteration, HPIPM-default KKT tolerances",
+            "batch_per_gpu": batch, "horizon": horizon, "variant": variant, "global_batch": batch * world,
+            "parallelism": f"dp{world} (independent instances, no collective on the solve path)",
+            "l2_flush_between_steps": True, "iterate_reset_between_steps": True}
+
+
+# ---------------------------------------------------------------------------- flops / bytes model
+def algorithmic_bytes_per_solve(nx, nu, N, s=8):
+    """read x0, yref, p; read + write the iterate."""
+    return s * ((nx + (nx + nu) + 25) + 2 * ((N + 1) * nx + N * nu))
+
+
+def algorithmic_flops_per_solve(nx, nu, N, n_fact):
+    nnzA, c_fJ = (59, 375) if nx == 17 else (36, 230)
+    nz = nx + nu
+    f_lin = 4 * (2 * nnzA * nz + c_fJ) + 8 * nx * (nz + 1)
+    f_ric = nx * nx * nz + nx * nz * nz + nz ** 3 / 3.0
+    f_sub = 2 * nz * nz + 4 * nx * nz
+    return N * f_lin + n_fact * N * f_ric + 2 * n_fact * N * f_sub
+
+
+# ---------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_steps(steps: int, warmup: int, batch: int, horizon: int, variant: int):
+    """Time the C oracle on all host cores: each step = the same 1,024-instance batch."""
+    from oracle import blaster_oracle as bo
+    from oracle import c_oracle as co
+    P = bo.canonical_problem(horizon, variant)
+    x0, yref, trim = workload(0, batch, variant)
+    orc = co.BatchRTI(P, batch)
+    times = []
+    for i in range(warmup + steps):
+        orc.reset(x0, trim)
+        t = time.perf_counter()
+        orc.solve(x0, yref)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    ok = float((orc.status == 0).mean())
+    return times, orc.nthreads, float(orc.iters.mean()), ok
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path for this solve.  acados/HPIPM/CasADi are not
+    installable here, so this is the C oracle port with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    times, cores, iters, ok = cpu_steps(args.steps, args.warmup, BATCH, HORIZON, VARIANT)
+    total = sum(times)
+    value = BATCH * len(times) / total
+    sample = f"{BATCH} instances (the full per-GPU batch) per step, {len(times)} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world, BATCH, HORIZON, VARIANT),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "mean_ipm_iters": iters, "converged_frac": ok},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from mpc_blaster_b200 import BlasterMPC
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, N = args.batch, HORIZON
+    mpc = BlasterMPC.canonical(N=N, batch=B, variant=VARIANT)
+    nx, nu = mpc.nx, mpc.nu
+    x0_h, yref_h, trim_h = workload(rank, B, VARIANT)
+    x0 = torch.as_tensor(x0_h, device=dev)
+    yref = torch.as_tensor(yref_h, device=dev)
+    trim = torch.as_tensor(trim_h, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
+    mpc.profile(True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        mpc.reset(x0, trim)
+        flush.zero_()
+        mpc.solve(x0, yref, want_traj=False)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k1_ms, k2_ms = [], []
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = mpc.kernel_launches()
+    launches = 0
+    for a, b in ev:
+        mpc.reset(x0, trim)
+        flush.zero_()
+        la = mpc.kernel_launches()
+        a.record()
+        u0, _, _, status = mpc.solve(x0, yref, want_traj=False)
+        b.record()
+        launches += mpc.kernel_launches() - la
+        t1, t2 = mpc.last_kernel_ms()
+        k1_ms.append(t1)
+        k2_ms.append(t2)
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    iters_mean = float(mpc.iters.double().mean().item())
+    ok_frac = float((status == 0).double().mean().item())
+
+    # ---- end to end through the host entry point of the C ABI
+    for _ in range(max(1, args.warmup // 2)):
+        mpc.reset(x0, trim)
+        mpc.solve_host(x0_h, yref_h)
+    barrier()
+    e2e_t = 0.0
+    for _ in range(args.steps):
+        mpc.reset(x0, trim)
+        flush.zero_()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        u0_h, _, _, st_h = mpc.solve_host(x0_h, yref_h)
+        e2e_t += time.perf_counter() - t
+    e2e_all = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_all, op=dist.ReduceOp.MAX)
+    e2e_t = float(e2e_all.item())
+    assert np.array_equal(u0_h, u0.cpu().numpy()), "host path and device path disagree"
+
+    # ---- final result gather (the only collective of the job)
+    if world > 1:
+        from mpc_blaster_b200.scheduler import gather_batch
+        all_u0 = gather_batch(u0, B * world)
+        assert all_u0.shape == (B * world, nu)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = B * world * args.steps / (total_ms * 1e-3)
+    e2e_value = B * world * args.steps / e2e_t
+    k2 = float(np.mean(k2_ms)) * 1e-3
+    k1 = float(np.mean(k1_ms)) * 1e-3
+    # roofline of the dominant kernel (qp_kernel)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback B200_PROFILING.md"
+    alg_bytes = algorithmic_bytes_per_solve(nx, nu, N) * B
+    achieved_gbs = alg_bytes / k2 / 1e9
+    fp64_peak = mpc.fp64_peak_tflops()
+    flops = algorithmic_flops_per_solve(nx, nu, N, iters_mean)
+    f_lin_only = algorithmic_flops_per_solve(nx, nu, N, 0)
+    qp_tflops = (flops - f_lin_only) * B / k2 / 1e12
+    lin_tflops = f_lin_only * B / k1 / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "qp_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        reps = max(2, args.cpu_steps)
+        times, cores, cpu_iters, cpu_ok = cpu_steps(reps, 1, B, N, VARIANT)
+        cpu = {"value": B * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"the same {B}-instance batch, {len(times)} repeats ({sum(times):.1f} s of wall time on {cores} threads)",
+               "mean_ipm_iters": cpu_iters, "converged_frac": cpu_ok}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(world, B, N, VARIANT),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x0_h.nbytes + yref_h.nbytes),
+                    "d2h_bytes_per_step": int(B * nu * 8 + 2 * B * 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "qp_kernel<17,6>", "achieved": achieved_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k2 * 1e3,
+                         "note": "latency/FP64-pipe bound path: see fp64 for the binding resource"},
+            "fp64": {"qp_kernel_tflops": qp_tflops, "linearize_kernel_tflops": lin_tflops, "peak_tflops_measured": fp64_peak,
+                     "qp_frac": qp_tflops / fp64_peak, "linearize_kernel_ms": k1 * 1e3,
+                     "algorithmic_mflop_per_solve": flops / 1e6},
+            "solver": {"mean_ipm_iters": iters_mean, "converged_frac": ok_frac,
+                       "p50_ms": float(np.percentile(step_ms, 50)), "p99_ms": float(np.percentile(step_ms, 99))},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "graft" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

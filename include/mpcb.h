@@ -114,6 +114,16 @@ int mpcb_set_iterate(mpcb_handle *h, const double *X, const double *U, int B, vo
  * BAt[B,N,nz,nx] = [B_k'; A_k'] and b[B,N,nx] (device pointers). */
 int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BAt, double *b, int B, void *stream);
 
+/* Profiling aid for bench.py: when enabled, CUDA events are recorded on the launching stream
+ * around the rollout kernel and the QP kernel of each solve (first workspace chunk);
+ * mpcb_last_kernel_ms waits for the last solve and returns the two durations. */
+int mpcb_profile(mpcb_handle *h, int enable);
+int mpcb_last_kernel_ms(mpcb_handle *h, float *ms_linearize, float *ms_qp);
+
+/* Measured FP64 FMA-pipe peak of a device (dependent-chain DFMA micro-kernel), in TFLOP/s:
+ * the roofline denominator for this path (MEASURED_PEAKS.json carries only HBM and bf16). */
+int mpcb_fp64_peak(int device, double *tflops);
+
 /* Number of kernels this library has launched since it was loaded (for bench accounting). */
 int64_t mpcb_kernel_launches(void);
 

@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(32 * WPB) qp_kernel(const __grid_constant__ Pa
                                                       int inst0, int B)
 {
     using L = Layout<NX, NU>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    QpSmem<NX, NU, double> *sm = reinterpret_cast<QpSmem<NX, NU, double> *>(smem_raw) + (threadIdx.x >> 5);
+    __shared__ __align__(16) QpSmem<NX, NU, double> sm_arr[WPB];
+    QpSmem<NX, NU, double> *sm = &sm_arr[threadIdx.x >> 5];
     const int N = P.N;
     const int li = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (li >= B) return;
@@ -153,7 +153,7 @@ __global__ void debug_copy_kernel(const __grid_constant__ Params P, const double
     const int e = (int)(r % (L::NZ * NX + NX));
     const double *wk = ws + (size_t)li * L::instance_stride(N) + (size_t)k * L::STAGE;
     const size_t inst = (size_t)inst0 + li;
-    if (e < L::NZ * NX) BAt[(inst * N + k) * (L::NZ * NX) + e] = wk[L::O_BAT + e];
+    if (e < L::NZ * NX) BAt[(inst * N + k) * (L::NZ * NX) + e] = wk[L::O_BAT + (e / NX) * L::LDB + e % NX];
     else b[(inst * N + k) * NX + (e - L::NZ * NX)] = wk[L::O_B + e - L::NZ * NX];
 }
 
@@ -184,6 +184,17 @@ __global__ void command_map_kernel(const double *__restrict__ x, const double *_
     }
 }
 
+// FP64 FMA-pipe micro-benchmark: 8 independent DFMA chains per thread.
+__global__ void fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ handle
@@ -203,6 +214,8 @@ struct mpcb_handle {
     double *d_stage = nullptr;
     size_t d_stage_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around K1 and K2 of the last solve (profiling)
+    bool profile = false;
     std::string err;
 };
 
@@ -263,19 +276,19 @@ template <int NX, int NU>
 int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
                         double *u0, int32_t *status, int32_t *iters, int B, cudaStream_t s)
 {
-    const size_t smem = sizeof(QpSmem<NX, NU, double>) * kWPB;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CK(h, cudaFuncSetAttribute(qp_kernel<NX, NU, kWPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static_assert(sizeof(QpSmem<NX, NU, double>) * kWPB <= 48 * 1024, "static shared memory limit");
+    const size_t smem = 0;
     for (int i0 = 0; i0 < B; i0 += h->ws_batch) {
         const int nb = (B - i0 < h->ws_batch) ? B - i0 : h->ws_batch;
         const long long warps = (long long)nb * h->N;
         const unsigned g1 = (unsigned)((warps * 32 + 127) / 128);
+        const bool prof = h->profile && i0 == 0;
+        if (prof) cudaEventRecord(h->ev[0], s);
         linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+        if (prof) cudaEventRecord(h->ev[1], s);
         qp_kernel<NX, NU, kWPB><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws,
                                                                                   u0, status, iters, i0, nb);
+        if (prof) cudaEventRecord(h->ev[2], s);
         g_launches += 2;
     }
     CK(h, cudaGetLastError());
@@ -377,6 +390,10 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     cudaMemset(h->ws, 0, (size_t)h->ws_batch * h->ws_stride * sizeof(double));
     e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { fail(nullptr, "cudaStreamCreate", e); mpcb_destroy(h); return -1; }
+    for (int i = 0; i < 3; i++) {
+        e = cudaEventCreate(&h->ev[i]);
+        if (e != cudaSuccess) { fail(nullptr, "cudaEventCreate", e); mpcb_destroy(h); return -1; }
+    }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { fail(nullptr, "init", e); mpcb_destroy(h); return -1; }
     *out = h;
@@ -392,6 +409,7 @@ int mpcb_destroy(mpcb_handle *h)
     cudaFree(h->d_stage);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return 0;
 }
@@ -578,6 +596,52 @@ int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BA
     }
     CK(h, cudaGetLastError());
     return 0;
+}
+
+int mpcb_profile(mpcb_handle *h, int enable)
+{
+    if (!h) return -1;
+    h->profile = enable != 0;
+    return 0;
+}
+
+int mpcb_last_kernel_ms(mpcb_handle *h, float *ms_linearize, float *ms_qp)
+{
+    if (!h || !h->profile) return fail(h, "profiling not enabled");
+    CK(h, cudaEventSynchronize(h->ev[2]));
+    if (ms_linearize) CK(h, cudaEventElapsedTime(ms_linearize, h->ev[0], h->ev[1]));
+    if (ms_qp) CK(h, cudaEventElapsedTime(ms_qp, h->ev[1], h->ev[2]));
+    return 0;
+}
+
+int mpcb_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return -1;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return -1;
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *out = nullptr;
+    if (cudaMalloc((void **)&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        cudaEventRecord(a);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-6);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && ms < best) best = ms;
+    }
+    g_launches += 5;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(out);
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 int mpcb_command_map(mpcb_handle *h, const double *x, const double *u0, double *quat, double *thrust, int B, void *stream)

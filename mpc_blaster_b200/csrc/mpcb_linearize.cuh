@@ -70,7 +70,7 @@ MPCB_DEV void linearize_warp(const Params &P, const T *__restrict__ Xk, const T 
 
     if (lane < NZ) {
         // row `lane` of [B'; A']
-        T *row = ws_stage + L::O_BAT + lane * NX;
+        T *row = ws_stage + L::O_BAT + lane * L::LDB;
         MPCB_UNROLL
         for (int i = 0; i < NX; i++) row[i] = acc[i];
     } else if (lane == NZ) {

@@ -7,211 +7,144 @@
 // reference blastermodel.py:274,284; cold start, acados_ocp_blasterModel.json
 // qp_solver_warm_start = 0).  Same algorithm class, new design:
 //   * lane j < NZ owns component j of the stage variable z_k = [du_k; dx_k] and row j of
-//     the stage matrices; stage matrices are staged in shared memory, vectors are
-//     exchanged through shared memory or shuffles;
-//   * the Riccati factor L_k (L_k L_k' = diag(H_k + barrier) + [B A]' P_{k+1} [B A]) is
-//     obtained by Householder LQ of [sqrt(diag) | [B A]' L_{k+1}] -- never forming the
-//     normal equations, so active *state* bounds (barrier ~ 1e15) cost eps*sqrt(barrier)
-//     instead of eps*barrier (the role of HPIPM's lq_fact);
-//   * the corrector is solved as a correction on top of the affine backward sweep, so per
-//     IPM iteration the stage matrices are read four times and L is written once.
+//     the stage matrices;
+//   * the Riccati factor L_k (L_k L_k' = diag(H_k + barrier) + [B A]' P_{k+1} [B A]) comes
+//     from a Householder LQ of [sqrt(diag) | [B A]' L_{k+1}] -- the normal equations are never
+//     formed, so active *state* bounds (barrier ~ 1e15) cost eps*sqrt(barrier) instead of
+//     eps*barrier (the role of HPIPM's lq_fact);
+//   * every stage-serial sweep runs out of shared memory: the next stage's record is
+//     fetched with cp.async into the other half of a double buffer while the current stage
+//     is being processed, so the recursion never waits on HBM/L2 latency;
+//   * everything that is elementwise in the stage index (box slacks/multipliers, step-length
+//     ratios, the update) is done in "flat" passes with independent loads, off the serial
+//     critical path; the corrector is solved as an increment on the affine backward sweep.
+//   Per IPM iteration the stage matrices are read four times and L is written once.
 #pragma once
 #include "mpcb_common.cuh"
 
 namespace mpcb {
 
+// Per-warp shared memory: two stage-record images (same offsets as the global record) plus
+// the data that is carried from one stage of a sweep to the next.
 template <int NX, int NU, typename T>
 struct QpSmem {
     using L = Layout<NX, NU>;
-    T BAt[L::NZ * L::LDB];
-    T Lxx[NX * NX];
-    T Lu[NU * L::NZP];
-    T vrow[2][L::NXP];
-    T sPi[L::NZP], sZ[L::NZP], sRb[L::NZP], sT1[L::NZP], sT2[L::NZP], sPv[L::NZP], sDx[L::NZP], sDz[L::NZP];
+    // every member is a multiple of 4 elements long, so all of them stay 32-byte aligned
+    alignas(32) T slot[2][L::STAGE];
+    T Lxx[L::LXX];       // factor of P_{k+1} (backward sweep), [NX][NX]; upper triangle stays zero
+    T vrow[2][L::NXP];   // Householder pivot row broadcast (double buffered)
+    T Lcol[L::NZ * L::NUP];  // first NU columns of the L_k being factorised, row-major [NZ][NUP]
+    T Linv[L::NUP];      // 1/diag(Luu)
+    T cPi[L::NXP], cZx[L::NXP], cPv[L::NXP], cDx[L::NXP];  // carried: pi_{k+1}, dx-part of z_{k+1}, p_{k+1}, dx_k
+    T sT1[L::NXP], sT2[L::NXP], sDz[L::NZP], sRb[L::NXP];
 };
 
-// Everything lane j needs to know about component j of stage k.
-template <typename T>
-struct StageVar {
-    bool var;    // is an optimisation variable (not the pinned x_0, not a u at stage N)
-    bool hasb;   // has box bounds
-    T H0, g, lb, ub;
+// static description of component j of stage k
+struct VarKind {
+    bool var;   // is an optimisation variable (not the pinned x_0, not a u at stage N)
+    bool hasb;  // has box bounds: lbu/ubu on stages 0..N-1, lbx/ubx on stages 1..N-1 [upstream D2]
 };
-
-// Gauss-Newton LINEAR_LS cost and bounds on the increments:
-// stage Hessian dt*diag(Q,R), terminal Q_t unscaled [upstream D1]; lbu/ubu on stages
-// 0..N-1, lbx/ubx on stages 1..N-1 [upstream D2]; x_0 pinned [upstream D3].
-template <int NX, int NU, typename T>
-MPCB_DEV StageVar<T> stage_var(const Params &P, int k, int j, const T *__restrict__ Xi, const T *__restrict__ Ui,
-                               const T *__restrict__ yref, int yref_per_stage)
+template <int NX, int NU>
+MPCB_DEV VarKind var_kind(int k, int j, int N)
 {
-    constexpr int NZ = NX + NU;
-    StageVar<T> s;
-    const int N = P.N;
-    s.var = false; s.hasb = false; s.H0 = T(1); s.g = T(0); s.lb = T(0); s.ub = T(0);
-    if (j >= NZ) return s;
-    const T *yr = yref + (yref_per_stage ? (size_t)k * NZ : 0);
-    if (j < NU) {
-        if (k < N) {
-            const T y = Ui[(size_t)k * NU + j];
-            const T w = (T)(P.dt * P.R[j]);
-            s.var = true; s.hasb = true; s.H0 = w; s.g = w * (y - yr[NX + j]);
-            s.lb = (T)P.lbu[j] - y; s.ub = (T)P.ubu[j] - y;
-        }
-    } else {
-        const int i = j - NU;
-        const T y = Xi[(size_t)k * NX + i];
-        const T w = (k < N) ? (T)(P.dt * P.Q[i]) : (T)P.Qt[i];
-        s.var = (k > 0); s.H0 = w; s.g = w * (y - yr[i]);
-        if (k >= 1 && k < N) { s.hasb = true; s.lb = (T)P.lbx[i] - y; s.ub = (T)P.ubx[i] - y; }
-    }
-    return s;
+    VarKind v;
+    if (j < NU) { v.var = k < N; v.hasb = k < N; }
+    else if (j < NX + NU) { v.var = k > 0; v.hasb = (k >= 1 && k < N); }
+    else { v.var = false; v.hasb = false; }
+    return v;
+}
+// Gauss-Newton LINEAR_LS Hessian diagonal: dt*diag(Q,R) on stages < N, Q_t at N [upstream D1]
+template <int NX, int NU, typename T>
+MPCB_DEV T hess_diag(const Params &P, int k, int j)
+{
+    if (j < NU) return (T)(P.dt * P.R[j]);
+    if (j < NX + NU) return (k < P.N) ? (T)(P.dt * P.Q[j - NU]) : (T)P.Qt[j - NU];
+    return T(1);
 }
 
-// Step of the box slacks / multipliers for Newton step dz (one component).
+// Step of the box slacks / multipliers for a Newton step dz (one component):
+//   dt_l = dz + r_dl, dt_u = -dz + r_du, dlam = -(r_m + lam*dt)/t
 template <typename T>
 struct BoxStep { T dtl, dtu, dll, dlu; };
 
 template <typename T>
-MPCB_DEV BoxStep<T> box_step(T z, T dz, T lb, T ub, T tl, T tu, T ll, T lu, T rml, T rmu)
+MPCB_DEV BoxStep<T> box_step(T z, T dz, T lb, T ub, T tl, T tu, T ll, T lu, T rml, T rmu, T itl, T itu)
 {
     BoxStep<T> b;
-    const T rdl = z - lb - tl, rdu = ub - z - tu;
-    b.dtl = dz + rdl;
-    b.dtu = -dz + rdu;
-    b.dll = -(rml + ll * b.dtl) / tl;
-    b.dlu = -(rmu + lu * b.dtu) / tu;
+    b.dtl = dz + (z - lb - tl);
+    b.dtu = -dz + (ub - z - tu);
+    b.dll = -(rml + ll * b.dtl) * itl;
+    b.dlu = -(rmu + lu * b.dtu) * itu;
     return b;
 }
 
+// largest step keeping v + a*dv >= 0, as its reciprocal (0 when dv >= 0)
 template <typename T>
-MPCB_DEV T ratio(T v, T dv) { return dv < T(0) ? -v / dv : T(HUGE_VAL); }
+MPCB_DEV T inv_ratio(T dv, T iv) { return dv < T(0) ? -dv * iv : T(0); }
 
-template <int NX, int NU, typename T>
-MPCB_DEV void load_BAt(QpSmem<NX, NU, T> &sm, const T *__restrict__ wk)
+// Inputs of the elementwise box computations for a batch of FBN consecutive stages
+// (component `lane` of each stage), loaded together so their latencies overlap.
+template <typename T, int FBN>
+struct BoxIn {
+    bool ok[FBN];   // has bounds (and the stage exists)
+    bool var[FBN];  // is an optimisation variable
+    T z[FBN], tl[FBN], tu[FBN], ll[FBN], lu[FBN], lb[FBN], ub[FBN], dza[FBN], dz[FBN];
+};
+template <int NX, int NU, typename T, int FBN, bool WITH_DZ>
+MPCB_DEV void load_box(BoxIn<T, FBN> &in, const T *__restrict__ ws, int k0, int kend, int N, int lane)
 {
     using L = Layout<NX, NU>;
-    const int lane = lane_id();
-    for (int idx = lane; idx < L::NZ * NX; idx += 32) sm.BAt[(idx / NX) * L::LDB + (idx % NX)] = wk[L::O_BAT + idx];
+    MPCB_UNROLL
+    for (int u = 0; u < FBN; u++) {
+        const int k = k0 + u;
+        const VarKind vk = var_kind<NX, NU>(k, lane, N);
+        in.ok[u] = (k < kend) && vk.hasb;
+        in.var[u] = (k < kend) && vk.var;
+        in.z[u] = in.dz[u] = in.dza[u] = in.lb[u] = in.ub[u] = in.ll[u] = in.lu[u] = T(0);
+        in.tl[u] = in.tu[u] = T(1);
+        const T *wk = ws + (size_t)k * L::STAGE;
+        if (in.var[u]) {
+            in.z[u] = wk[L::O_Z + lane];
+            if (WITH_DZ) in.dz[u] = wk[L::O_DZ + lane];
+        }
+        if (in.ok[u]) {
+            in.tl[u] = wk[L::O_TL + lane]; in.tu[u] = wk[L::O_TU + lane];
+            in.ll[u] = wk[L::O_LL + lane]; in.lu[u] = wk[L::O_LUP + lane];
+            in.lb[u] = wk[L::O_LB + lane]; in.ub[u] = wk[L::O_UB + lane];
+            in.dza[u] = wk[L::O_DZA + lane];
+        }
+    }
 }
 
-// t2 = P r + p with P = Lxx Lxx' (Lxx in shared memory); r in sm.sRb, p in sm.sPv, result in sm.sT2.
+// t2 = P r + p with P = Lxx Lxx' (Lxx in shared memory, zero upper triangle);
+// r in sm.sRb, p in sm.cPv, result in sm.sT2.
 template <int NX, int NU, typename T>
 MPCB_DEV void apply_P(QpSmem<NX, NU, T> &sm)
 {
     const int lane = lane_id();
-    if (lane < NX) {
-        T a = T(0);
-        for (int j = lane; j < NX; j++) a += sm.Lxx[j * NX + lane] * sm.sRb[j];
-        sm.sT1[lane] = a;
+    const int c = lane < NX ? lane : 0;
+    T a0 = T(0), a1 = T(0);
+    MPCB_UNROLL
+    for (int j = 0; j + 1 < NX; j += 2) {
+        a0 += sm.Lxx[j * NX + c] * sm.sRb[j];
+        a1 += sm.Lxx[(j + 1) * NX + c] * sm.sRb[j + 1];
     }
+    if (NX & 1) a0 += sm.Lxx[(NX - 1) * NX + c] * sm.sRb[NX - 1];
+    if (lane < NX) sm.sT1[lane] = a0 + a1;
     warp_sync();
-    if (lane < NX) {
-        T a = sm.sPv[lane];
-        for (int c = 0; c <= lane; c++) a += sm.Lxx[lane * NX + c] * sm.sT1[c];
-        sm.sT2[lane] = a;
+    T b0 = sm.cPv[c], b1 = T(0);
+    MPCB_UNROLL
+    for (int j = 0; j + 1 < NX; j += 2) {
+        b0 += sm.Lxx[c * NX + j] * sm.sT1[j];
+        b1 += sm.Lxx[c * NX + j + 1] * sm.sT1[j + 1];
     }
+    if (NX & 1) b0 += sm.Lxx[c * NX + NX - 1] * sm.sT1[NX - 1];
+    if (lane < NX) sm.sT2[lane] = b0 + b1;
     warp_sync();
-}
-
-// One forward sweep (affine: FINAL=false, corrector: FINAL=true).  Returns the largest
-// admissible step and, for the affine sweep, the three sums that give mu_aff(alpha).
-template <int NX, int NU, typename T, bool FINAL>
-MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict__ ws, const T *__restrict__ Xi,
-                            const T *__restrict__ Ui, const T *__restrict__ yref, int yps, T sigmu, T &amax, T &s1,
-                            T &s2)
-{
-    using L = Layout<NX, NU>;
-    constexpr int NZ = L::NZ;
-    const int lane = lane_id();
-    const int N = P.N;
-    T amin = T(HUGE_VAL), acc1 = T(0), acc2 = T(0);
-    if (lane < NX) sm.sDx[lane] = T(0);
-    warp_sync();
-    for (int k = 0; k < N; k++) {
-        T *wk = ws + (size_t)k * L::STAGE;
-        T *wk1 = wk + L::STAGE;
-        load_BAt<NX, NU, T>(sm, wk);
-        for (int idx = lane; idx < NU * L::NZP; idx += 32) sm.Lu[idx] = wk[L::O_LU + idx];
-        if (FINAL)
-            for (int idx = lane; idx < NX * NX; idx += 32) sm.Lxx[idx] = wk1[L::O_LXX + idx];
-        T invd[NU];
-        MPCB_UNROLL
-        for (int c = 0; c < NU; c++) invd[c] = wk[L::O_INVD + c];
-        warp_sync();
-        // du = -Luu^{-T} (lvec + Lxu' dx)
-        T yy = T(0);
-        if (lane < NU) {
-            T a = wk[L::O_LVEC + lane];
-            for (int i = 0; i < NX; i++) a += sm.Lu[lane * L::NZP + NU + i] * sm.sDx[i];
-            yy = -a;
-        }
-        T du = T(0);
-        MPCB_UNROLL
-        for (int i = NU - 1; i >= 0; i--) {
-            const T dui = warp_shfl(yy, i) * invd[i];
-            if (lane == i) du = dui;
-            if (lane < i) yy -= sm.Lu[lane * L::NZP + i] * dui;
-        }
-        T dz = T(0);
-        if (lane < NU) dz = du;
-        else if (lane < NZ) dz = sm.sDx[lane - NU];
-        if (lane < NZ) {
-            wk[(FINAL ? L::O_DZ : L::O_DZA) + lane] = dz;
-            sm.sDz[lane] = dz;
-        }
-        warp_sync();
-        // dx_{k+1} = rb_k + [B A] dz_k
-        T dxn = T(0);
-        if (lane < NX) {
-            dxn = wk[L::O_RB + lane];
-            for (int j = 0; j < NZ; j++) dxn += sm.BAt[j * L::LDB + lane] * sm.sDz[j];
-            sm.sRb[lane] = dxn;  // input of apply_P below
-            if (FINAL) sm.sPv[lane] = wk1[L::O_PV + lane];
-        }
-        // step-length bookkeeping for the bounded components of stage k
-        {
-            const StageVar<T> sv = stage_var<NX, NU, T>(P, k, lane, Xi, Ui, yref, yps);
-            if (sv.hasb) {
-                const T z = wk[L::O_Z + lane], tl = wk[L::O_TL + lane], tu = wk[L::O_TU + lane];
-                const T ll = wk[L::O_LL + lane], lu = wk[L::O_LUP + lane];
-                T rml = ll * tl, rmu = lu * tu;
-                if (FINAL) {
-                    const T dza = wk[L::O_DZA + lane];
-                    const BoxStep<T> a = box_step(z, dza, sv.lb, sv.ub, tl, tu, ll, lu, rml, rmu);
-                    rml += a.dll * a.dtl - sigmu;
-                    rmu += a.dlu * a.dtu - sigmu;
-                }
-                const BoxStep<T> b = box_step(z, dz, sv.lb, sv.ub, tl, tu, ll, lu, rml, rmu);
-                amin = fmin(amin, fmin(fmin(ratio(tl, b.dtl), ratio(tu, b.dtu)), fmin(ratio(ll, b.dll), ratio(lu, b.dlu))));
-                if (!FINAL) {
-                    acc1 += ll * b.dtl + tl * b.dll + lu * b.dtu + tu * b.dlu;
-                    acc2 += b.dll * b.dtl + b.dlu * b.dtu;
-                }
-            }
-        }
-        warp_sync();
-        if (FINAL) {
-            // dpi_{k+1} = P_{k+1} dx_{k+1} + p_{k+1}
-            apply_P<NX, NU, T>(sm);
-            if (lane < NX) wk1[L::O_DPI + lane] = sm.sT2[lane];
-        }
-        if (lane < NX) sm.sDx[lane] = dxn;
-        warp_sync();
-    }
-    // terminal stage: dz_N = [0; dx_N], no bounds
-    {
-        T *wN = ws + (size_t)N * L::STAGE;
-        if (lane < NZ) wN[(FINAL ? L::O_DZ : L::O_DZA) + lane] = (lane < NU) ? T(0) : sm.sDx[lane - NU];
-    }
-    warp_sync();
-    amax = warp_min(amin);
-    s1 = warp_sum(acc1);
-    s2 = warp_sum(acc2);
 }
 
 // Forward substitution with the first NU columns of L_k held row-wise in registers:
-// on return lanes c < NU hold lvec_c = (Luu^{-1} l_u)_c and lanes NU.. hold p_k.
+// on return lanes c < NU hold lvec_c = (Luu^{-1} l_u)_c and lanes NU.. hold l_x - Lxu lvec.
 template <int NU, typename T>
 MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
 {
@@ -224,6 +157,112 @@ MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
         if (lane > c && lane < nz) out -= Lu[c] * lc;
     }
     return out;
+}
+
+// One forward sweep: dz_k = [du_k; dx_k] with du_k = -Luu^{-T}(lvec_k + Lxu' dx_k),
+// dx_{k+1} = r_k + [B A] dz_k.  FINAL additionally produces dpi_{k+1} = P_{k+1} dx_{k+1} + p_{k+1}.
+template <int NX, int NU, typename T, bool FINAL>
+MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict__ ws)
+{
+    using L = Layout<NX, NU>;
+    constexpr int NZ = L::NZ;
+    constexpr int O_OUT = FINAL ? L::O_DZ : L::O_DZA;
+    const int lane = lane_id();
+    const int N = P.N;
+    // record k: [BAt | Lu | invd | lvec | rb]; FINAL: also [Lxx | pv] of record k+1
+    constexpr int RUN1 = L::O_Z;
+    async_copy(sm.slot[0], ws, RUN1);
+    if (FINAL) async_copy(sm.slot[0] + L::O_LXX, ws + L::STAGE + L::O_LXX, L::LXX + L::NXP);
+    async_commit();
+    if (lane < NX) sm.cDx[lane] = T(0);
+    for (int k = 0; k < N; k++) {
+        T *wk = ws + (size_t)k * L::STAGE;
+        const T *s = sm.slot[k & 1];
+        if (k + 1 < N) {
+            T *nx = sm.slot[(k + 1) & 1];
+            async_copy(nx, wk + L::STAGE, RUN1);
+            if (FINAL) async_copy(nx + L::O_LXX, wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP);
+            async_commit();
+            async_wait<1>();
+        } else {
+            async_wait<0>();
+        }
+        warp_sync();
+        // du = -Luu^{-T} (lvec + Lxu' dx)
+        T yy = T(0);
+        if (lane < NU) {
+            T a0 = s[L::O_LVEC + lane], a1 = T(0), a2 = T(0), a3 = T(0);
+            const T *col = s + L::O_LU + lane * L::NZP + NU;
+            MPCB_UNROLL
+            for (int i = 0; i + 3 < NX; i += 4) {
+                a0 += col[i] * sm.cDx[i]; a1 += col[i + 1] * sm.cDx[i + 1];
+                a2 += col[i + 2] * sm.cDx[i + 2]; a3 += col[i + 3] * sm.cDx[i + 3];
+            }
+            MPCB_UNROLL
+            for (int i = NX & ~3; i < NX; i++) a0 += col[i] * sm.cDx[i];
+            yy = -((a0 + a1) + (a2 + a3));
+        }
+        T du = T(0);
+        MPCB_UNROLL
+        for (int i = NU - 1; i >= 0; i--) {
+            const T dui = warp_shfl(yy, i) * s[L::O_INVD + i];
+            if (lane == i) du = dui;
+            if (lane < i) yy -= s[L::O_LU + lane * L::NZP + i] * dui;
+        }
+        T dz = T(0);
+        if (lane < NU) dz = du;
+        else if (lane < NZ) dz = sm.cDx[lane - NU];
+        if (lane < NZ) {
+            wk[O_OUT + lane] = dz;
+            sm.sDz[lane] = dz;
+        }
+        warp_sync();
+        // dx_{k+1} = rb_k + [B A] dz_k
+        if (lane < NX) {
+            T a0 = s[L::O_RB + lane], a1 = T(0), a2 = T(0), a3 = T(0);
+            MPCB_UNROLL
+            for (int j = 0; j + 3 < NZ; j += 4) {
+                a0 += s[L::O_BAT + j * L::LDB + lane] * sm.sDz[j];
+                a1 += s[L::O_BAT + (j + 1) * L::LDB + lane] * sm.sDz[j + 1];
+                a2 += s[L::O_BAT + (j + 2) * L::LDB + lane] * sm.sDz[j + 2];
+                a3 += s[L::O_BAT + (j + 3) * L::LDB + lane] * sm.sDz[j + 3];
+            }
+            MPCB_UNROLL
+            for (int j = NZ & ~3; j < NZ; j++) a0 += s[L::O_BAT + j * L::LDB + lane] * sm.sDz[j];
+            const T dxn = (a0 + a1) + (a2 + a3);
+            sm.cDx[lane] = dxn;
+            if (FINAL) {
+                // dpi_{k+1} = Lxx_{k+1} (Lxx_{k+1}' dx_{k+1}) + p_{k+1}
+                sm.sRb[lane] = dxn;
+            }
+        }
+        warp_sync();
+        if (FINAL) {
+            const int c = lane < NX ? lane : 0;
+            const T *Lx = s + L::O_LXX;
+            T a0 = T(0), a1 = T(0);
+            MPCB_UNROLL
+            for (int j = 0; j + 1 < NX; j += 2) {
+                a0 += Lx[j * NX + c] * sm.sRb[j];
+                a1 += Lx[(j + 1) * NX + c] * sm.sRb[j + 1];
+            }
+            if (NX & 1) a0 += Lx[(NX - 1) * NX + c] * sm.sRb[NX - 1];
+            if (lane < NX) sm.sT1[lane] = a0 + a1;
+            warp_sync();
+            T b0 = s[L::O_PV + c], b1 = T(0);
+            MPCB_UNROLL
+            for (int j = 0; j + 1 < NX; j += 2) {
+                b0 += Lx[c * NX + j] * sm.sT1[j];
+                b1 += Lx[c * NX + j + 1] * sm.sT1[j + 1];
+            }
+            if (NX & 1) b0 += Lx[c * NX + NX - 1] * sm.sT1[NX - 1];
+            if (lane < NX) wk[L::STAGE + L::O_DPI + lane] = b0 + b1;
+            warp_sync();
+        }
+    }
+    // terminal stage: dz_N = [0; dx_N]
+    if (lane < NZ) ws[(size_t)N * L::STAGE + O_OUT + lane] = (lane < NU) ? T(0) : sm.cDx[lane - NU];
+    warp_sync();
 }
 
 // The whole QP solve for one instance.  On return the persistent iterate Xi/Ui has taken
@@ -240,35 +279,53 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
     const int N = P.N;
     const T thr0 = (T)P.ipm_thr0, mu0 = (T)P.ipm_mu0;
     const T nb = (T)(2 * NU * N + 2 * NX * (N - 1));
+    constexpr int FB = 4;  // stages per batch in the flat (elementwise) passes
 
     for (int idx = lane; idx < NX * NX; idx += 32) sm.Lxx[idx] = T(0);
 
-    // ---------------- cold start [upstream D8]: z = 0 (dx_0 pinned), pi = 0, t >= thr0, lam = mu0/t
+    // ---------------- F0: QP data and cold start [upstream D8]: z = 0 (dx_0 pinned), pi = 0,
+    // t >= thr0, lam = mu0/t.  Cost gradient and bounds on the increments.
     T eg = T(0), eb = T(0), ed = T(0);
+    MPCB_UNROLL4
     for (int k = 0; k <= N; k++) {
         T *wk = ws + (size_t)k * L::STAGE;
-        const StageVar<T> sv = stage_var<NX, NU, T>(P, k, lane, Xi, Ui, yref, yps);
-        T z = T(0);
-        if (k == 0 && lane >= NU && lane < NZ) z = x0[lane - NU] - Xi[lane - NU];
+        const VarKind vk = var_kind<NX, NU>(k, lane, N);
+        const T H0 = hess_diag<NX, NU, T>(P, k, lane);
+        const T *yr = yref + (yps ? (size_t)k * NZ : 0);
+        T y = T(0), g = T(0), lb = T(0), ub = T(0), z = T(0);
+        if (lane < NU) {
+            if (k < N) {
+                y = Ui[(size_t)k * NU + lane];
+                g = H0 * (y - yr[NX + lane]);
+                lb = (T)P.lbu[lane] - y; ub = (T)P.ubu[lane] - y;
+            }
+        } else if (lane < NZ) {
+            const int i = lane - NU;
+            y = Xi[(size_t)k * NX + i];
+            g = H0 * (y - yr[i]);
+            if (vk.hasb) { lb = (T)P.lbx[i] - y; ub = (T)P.ubx[i] - y; }
+            if (k == 0) z = x0[i] - y;  // [upstream D3] dx_0 = x0 - X_0
+        }
         T tl = T(1), tu = T(1), ll = T(0), lu = T(0);
-        if (sv.hasb) {
-            tl = fmax(z - sv.lb, thr0);
-            tu = fmax(sv.ub - z, thr0);
+        if (vk.hasb) {
+            tl = fmax(z - lb, thr0);
+            tu = fmax(ub - z, thr0);
             ll = mu0 / tl;
             lu = mu0 / tu;
-            ed = fmax(ed, fmax(fabs(z - sv.lb - tl), fabs(sv.ub - z - tu)));
+            ed = fmax(ed, fmax(fabs(z - lb - tl), fabs(ub - z - tu)));
         }
-        if (sv.var) eg = fmax(eg, fabs(sv.H0 * z + sv.g - ll + lu));
+        if (vk.var) eg = fmax(eg, fabs(H0 * z + g - ll + lu));
         if (lane < NZ) {
             wk[L::O_Z + lane] = z; wk[L::O_TL + lane] = tl; wk[L::O_TU + lane] = tu;
             wk[L::O_LL + lane] = ll; wk[L::O_LUP + lane] = lu;
+            wk[L::O_LB + lane] = lb; wk[L::O_UB + lane] = ub; wk[L::O_G + lane] = g;
         }
         if (lane < NX) {
             wk[L::O_PI + lane] = T(0);
             if (k < N) {
                 T rb = wk[L::O_B + lane];
                 if (k == 0)
-                    for (int i = 0; i < NX; i++) rb += wk[L::O_BAT + (NU + i) * NX + lane] * (x0[i] - Xi[i]);
+                    for (int i = 0; i < NX; i++) rb += wk[L::O_BAT + (NU + i) * L::LDB + lane] * (x0[i] - Xi[i]);
                 eb = fmax(eb, fabs(rb));
             }
         }
@@ -284,68 +341,93 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             status = ST_OK;
             break;
         }
-        int fail = 0;
-        // ================= S1: backward sweep -- residuals, factorisation, affine RHS
+        // ================= S1: backward sweep -- residuals, factorisation, affine right-hand side
+        // record k: run A = [BAt], run B = [z tl tu ll lu lb ub g pi b]
+        constexpr int RUNB = L::O_C1 - L::O_Z;
+        T last_sig = T(1);
         {
+            // terminal stage N: no inputs, no bounds; L_N = sqrt(Q_t), p_N = q_N
             T *wN = ws + (size_t)N * L::STAGE;
-            const StageVar<T> sv = stage_var<NX, NU, T>(P, N, lane, Xi, Ui, yref, yps);
-            T q = T(0);
+            async_copy(sm.slot[(N - 1) & 1], wN - L::STAGE, L::BAT);
+            async_copy(sm.slot[(N - 1) & 1] + L::O_Z, wN - L::STAGE + L::O_Z, RUNB);
+            async_commit();
             if (lane >= NU && lane < NZ) {
                 const int i = lane - NU;
-                q = sv.H0 * wN[L::O_Z + lane] + sv.g - wN[L::O_PI + i];
-                const T d = sqrt(sv.H0);
+                const T H0 = hess_diag<NX, NU, T>(P, N, lane);
+                const T zN = wN[L::O_Z + lane], piN = wN[L::O_PI + i];
+                const T q = H0 * zN + wN[L::O_G + lane] - piN;
+                sm.Lxx[i * NX + i] = sqrt(H0);
+                MPCB_UNROLL
                 for (int c = 0; c < NX; c++)
-                    if (c <= i) sm.Lxx[i * NX + c] = (c == i) ? d : T(0);
-                sm.sPv[i] = q;
+                    if (c < i) sm.Lxx[i * NX + c] = T(0);
+                sm.cPv[i] = q;
+                sm.cPi[i] = piN;
+                sm.cZx[i] = zN;
                 wN[L::O_PV + i] = q;
             }
-            if (lane < NZ) wN[L::O_Q + lane] = q;
             warp_sync();
             for (int idx = lane; idx < NX * NX; idx += 32) wN[L::O_LXX + idx] = sm.Lxx[idx];
         }
         for (int k = N - 1; k >= 0; k--) {
             T *wk = ws + (size_t)k * L::STAGE;
-            T *wk1 = wk + L::STAGE;
-            load_BAt<NX, NU, T>(sm, wk);
-            if (lane < NX) sm.sPi[lane] = wk1[L::O_PI + lane];
-            const T zj = (lane < NZ) ? wk[L::O_Z + lane] : T(0);
-            if (lane < NZ) sm.sZ[lane] = zj;
+            const T *s = sm.slot[k & 1];
+            if (k > 0) {
+                T *nx = sm.slot[(k - 1) & 1];
+                async_copy(nx, wk - L::STAGE, L::BAT);
+                async_copy(nx + L::O_Z, wk - L::STAGE + L::O_Z, RUNB);
+                async_commit();
+                async_wait<1>();
+            } else {
+                async_wait<0>();
+            }
             warp_sync();
+            const int jr = lane < NZ ? lane : 0;
             T brow[NX];
             MPCB_UNROLL
-            for (int c = 0; c < NX; c++) brow[c] = (lane < NZ) ? sm.BAt[lane * L::LDB + c] : T(0);
-            const StageVar<T> sv = stage_var<NX, NU, T>(P, k, lane, Xi, Ui, yref, yps);
-            T Hd = sv.H0, q = T(0);
+            for (int c = 0; c < NX; c++) brow[c] = s[L::O_BAT + jr * L::LDB + c];
+            const VarKind vk = var_kind<NX, NU>(k, lane, N);
+            const T zj = s[L::O_Z + jr];
+            T Hd = hess_diag<NX, NU, T>(P, k, lane), q = T(0);
             {
-                T rg = T(0);
                 T ll = T(0), lu = T(0), tl = T(1), tu = T(1);
-                if (sv.hasb) {
-                    tl = wk[L::O_TL + lane]; tu = wk[L::O_TU + lane]; ll = wk[L::O_LL + lane]; lu = wk[L::O_LUP + lane];
-                }
-                if (sv.var) {
-                    rg = sv.H0 * zj + sv.g - ll + lu;
+                if (vk.hasb) { tl = s[L::O_TL + lane]; tu = s[L::O_TU + lane]; ll = s[L::O_LL + lane]; lu = s[L::O_LUP + lane]; }
+                if (vk.var) {
+                    T r0 = Hd * zj + s[L::O_G + lane] - ll + lu, r1 = T(0);
                     MPCB_UNROLL
-                    for (int c = 0; c < NX; c++) rg += brow[c] * sm.sPi[c];
-                    if (lane >= NU) rg -= wk[L::O_PI + lane - NU];
+                    for (int c = 0; c + 1 < NX; c += 2) { r0 += brow[c] * sm.cPi[c]; r1 += brow[c + 1] * sm.cPi[c + 1]; }
+                    if (NX & 1) r0 += brow[NX - 1] * sm.cPi[NX - 1];
+                    q = r0 + r1;
+                    if (lane >= NU) q -= s[L::O_PI + lane - NU];
                 }
-                q = rg;
-                if (sv.hasb) {
-                    const T rdl = zj - sv.lb - tl, rdu = sv.ub - zj - tu;
-                    Hd += ll / tl + lu / tu;
-                    // affine right-hand side: rm = lam*t
-                    q += (ll * tl + ll * rdl) / tl - (lu * tu + lu * rdu) / tu;
+                if (vk.hasb) {
+                    const T itl = fast_rcp(tl), itu = fast_rcp(tu);
+                    const T rdl = zj - s[L::O_LB + lane] - tl, rdu = s[L::O_UB + lane] - zj - tu;
+                    Hd += ll * itl + lu * itu;
+                    // affine right-hand side (r_m = lam*t):  q += lam_l + lam_l r_dl/t_l - lam_u - lam_u r_du/t_u
+                    q += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
                 }
             }
+            // r_k = b_k + [B A] z_k - dx-part of z_{k+1}
             if (lane < NX) {
-                T rb = wk[L::O_B + lane] - wk1[L::O_Z + NU + lane];
-                for (int j = 0; j < NZ; j++) rb += sm.BAt[j * L::LDB + lane] * sm.sZ[j];
+                T a0 = s[L::O_B + lane] - sm.cZx[lane], a1 = T(0), a2 = T(0), a3 = T(0);
+                MPCB_UNROLL
+                for (int j = 0; j + 3 < NZ; j += 4) {
+                    a0 += s[L::O_BAT + j * L::LDB + lane] * s[L::O_Z + j];
+                    a1 += s[L::O_BAT + (j + 1) * L::LDB + lane] * s[L::O_Z + j + 1];
+                    a2 += s[L::O_BAT + (j + 2) * L::LDB + lane] * s[L::O_Z + j + 2];
+                    a3 += s[L::O_BAT + (j + 3) * L::LDB + lane] * s[L::O_Z + j + 3];
+                }
+                MPCB_UNROLL
+                for (int j = NZ & ~3; j < NZ; j++) a0 += s[L::O_BAT + j * L::LDB + lane] * s[L::O_Z + j];
+                const T rb = (a0 + a1) + (a2 + a3);
                 wk[L::O_RB + lane] = rb;
                 sm.sRb[lane] = rb;
             }
-            if (lane < NZ) wk[L::O_Q + lane] = q;
             warp_sync();
-            // t2 = P_{k+1} rb + p_{k+1}
+            // t2 = P_{k+1} r_k + p_{k+1}
             apply_P<NX, NU, T>(sm);
+            // carry this stage's pi and dx-part of z to stage k-1 (cPi / cZx were consumed above)
+            if (lane < NX) { sm.cPi[lane] = s[L::O_PI + lane]; sm.cZx[lane] = s[L::O_Z + NU + lane]; }
             // W = [B A]' Lxx_{k+1}   (row `lane`)
             T w[NX];
             MPCB_UNROLL
@@ -356,60 +438,69 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
                 w[c] = a;
             }
             const T dsq = sqrt(Hd);
-            T Lu[NU], invd[NU];
-            // Householder LQ of [diag(dsq) | W]; at stage 0 only the u-block is needed
+            // Householder LQ of [diag(dsq) | W], one pivot row per step:
+            //   sigma^2 = Hd_j + |w_j|^2,  L_ij = (w_i . w_j)/sigma,
+            //   w_i -= L_ij * kappa * w_j,  kappa = 1/(sigma + dsq_j) = (sigma - dsq_j)/|w_j|^2
+            // (the second form lets 1/|w_j|^2 be computed beside rsqrt(sigma^2) instead of after it;
+            // its cancellation error is O(eps |w_i|)).  The loop is deliberately
+            // NOT unrolled: its body (~2 KB of SASS) then stays in the L0 instruction cache, which
+            // matters at 1-2 resident warps per scheduler.  Column j of L goes to shared memory
+            // (sm.Lcol, [NZ][NZ+1]); at stage 0 only the u-block is needed (x_0 is pinned).
             const int jend = (k == 0) ? NU : NZ;
+            T sig = T(1);
+            if (lane >= NZ) {
+                MPCB_UNROLL
+                for (int c = 0; c < NX; c++) w[c] = T(0);  // idle lanes carry zero rows: no masks needed below
+            }
+            const sptr vr0 = sptr_of(sm.vrow[0]);
+            // column j of L goes to sm.Lcol ([NZ][NUP], j < NU) or straight into sm.Lxx (j >= NU, lower part)
+            const sptr lu_row = sptr_of(sm.Lcol + (lane < NZ ? lane : 0) * L::NUP);
+            const sptr lxx_row = sptr_add(sptr_of(sm.Lxx + (lane >= NU && lane < NZ ? lane - NU : 0) * NX), -NU);
+            const sptr linv = sptr_of(sm.Linv);
+            MPCB_NOUNROLL
+            for (int j = 0; j < jend; j++) {
+                const sptr vr = sptr_add(vr0, (j & 1) * L::NXP);
+                const T hdj = warp_shfl(Hd, j), dsj = warp_shfl(dsq, j);
+                const bool piv = (lane == j);
+                sp_row_store<0, NX>(vr, w, piv);
+                warp_sync();
+                T v[NX];
+                sp_row_load<0, NX>(vr, v);
+                T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+                MPCB_UNROLL
+                for (int c = 0; c + 3 < NX; c += 4) {
+                    d0 += v[c] * w[c]; d1 += v[c + 1] * w[c + 1]; d2 += v[c + 2] * w[c + 2]; d3 += v[c + 3] * w[c + 3];
+                }
+                MPCB_UNROLL
+                for (int c = NX & ~3; c < NX; c++) d0 += v[c] * w[c];
+                const T dot = (d0 + d1) + (d2 + d3);
+                const T djj = warp_shfl(dot, j);
+                const T s2v = hdj + djj;
+                const T rs = fast_rsqrt(s2v);
+                const T idjj = fast_rcp(djj);
+                sig = s2v * rs;
+                const T kap = (djj > T(0)) ? (sig - dsj) * idjj : T(0);
+                const T lij = (lane > j) ? dot * rs : T(0);
+                const T f = lij * kap;
+                MPCB_UNROLL
+                for (int c = 0; c < NX; c++) w[c] -= f * v[c];
+                const bool upart = j < NU;
+                sp_st1<0>(sptr_add(upart ? lu_row : lxx_row, j), piv ? sig : lij, lane < NZ && (upart || lane >= j));
+                sp_st1<0>(sptr_add(linv, j), rs, piv && upart);
+            }
+            last_sig = sig;
+            warp_sync();
+            T Lu[NU], invd[NU];
             MPCB_UNROLL
-            for (int j = 0; j < NU; j++) {
-                T *vr = sm.vrow[j & 1];
-                if (lane == j) {
-                    MPCB_UNROLL
-                    for (int c = 0; c < NX; c++) vr[c] = w[c];
-                }
-                warp_sync();
-                T dot = T(0);
-                MPCB_UNROLL
-                for (int c = 0; c < NX; c++) dot += vr[c] * w[c];
-                const T s2v = warp_shfl(Hd, j) + warp_shfl(dot, j);
-                const T rs = fast_rsqrt(s2v);
-                const T sig = s2v * rs;
-                const T v0 = warp_shfl(dsq, j) + sig;
-                const T beta = rs * fast_rcp(v0);
-                if (!(s2v > T(0)) || !(s2v < T(HUGE_VAL))) fail = 1;
-                const T f = (lane > j && lane < NZ) ? beta * dot : T(0);
-                MPCB_UNROLL
-                for (int c = 0; c < NX; c++) w[c] -= f * vr[c];
-                Lu[j] = (lane == j) ? sig : f * v0;
-                invd[j] = rs;
-            }
-            for (int j = NU; j < jend; j++) {
-                T *vr = sm.vrow[j & 1];
-                if (lane == j) {
-                    MPCB_UNROLL
-                    for (int c = 0; c < NX; c++) vr[c] = w[c];
-                }
-                warp_sync();
-                T dot = T(0);
-                MPCB_UNROLL
-                for (int c = 0; c < NX; c++) dot += vr[c] * w[c];
-                const T s2v = warp_shfl(Hd, j) + warp_shfl(dot, j);
-                const T rs = fast_rsqrt(s2v);
-                const T sig = s2v * rs;
-                const T v0 = warp_shfl(dsq, j) + sig;
-                const T beta = rs * fast_rcp(v0);
-                if (!(s2v > T(0)) || !(s2v < T(HUGE_VAL))) fail = 1;
-                const T f = (lane > j && lane < NZ) ? beta * dot : T(0);
-                MPCB_UNROLL
-                for (int c = 0; c < NX; c++) w[c] -= f * vr[c];
-                if (lane >= j && lane < NZ) sm.Lxx[(lane - NU) * NX + (j - NU)] = (lane == j) ? sig : f * v0;
-            }
+            for (int c = 0; c < NU; c++) { Lu[c] = sm.Lcol[(lane < NZ ? lane : 0) * L::NUP + c]; invd[c] = sm.Linv[c]; }
             // affine backward vectors: l = q + [B A]' t2
-            T l = q;
+            T l0 = q, l1 = T(0);
             MPCB_UNROLL
-            for (int c = 0; c < NX; c++) l += brow[c] * sm.sT2[c];
-            l = fwd_subst<NU, T>(l, Lu, invd, NZ);
+            for (int c = 0; c + 1 < NX; c += 2) { l0 += brow[c] * sm.sT2[c]; l1 += brow[c + 1] * sm.sT2[c + 1]; }
+            if (NX & 1) l0 += brow[NX - 1] * sm.sT2[NX - 1];
+            const T l = fwd_subst<NU, T>(l0 + l1, Lu, invd, NZ);
             if (lane < NU) wk[L::O_LVEC + lane] = l;
-            else if (lane < NZ) { wk[L::O_PV + lane - NU] = l; sm.sPv[lane - NU] = l; }
+            else if (lane < NZ) { wk[L::O_PV + lane - NU] = l; sm.cPv[lane - NU] = l; }
             if (lane < NZ) {
                 MPCB_UNROLL
                 for (int c = 0; c < NU; c++) wk[L::O_LU + c * L::NZP + lane] = Lu[c];
@@ -424,76 +515,155 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             if (k > 0)
                 for (int idx = lane; idx < NX * NX; idx += 32) wk[L::O_LXX + idx] = sm.Lxx[idx];
         }
-        if (warp_or(fail)) { status = ST_QPFAIL; break; }
+        // a breakdown (NaN) anywhere in the recursion propagates into the last pivot of stage 0
+        if (!(last_sig == last_sig) || !(last_sig < T(HUGE_VAL))) { status = ST_QPFAIL; break; }
 
         // ================= S2: forward sweep, affine step
-        T a_aff, s1, s2;
-        forward_sweep<NX, NU, T, false>(P, sm, ws, Xi, Ui, yref, yps, T(0), a_aff, s1, s2);
-        a_aff = fmin(T(1), a_aff);
-        const T mu_aff = (mu * nb + a_aff * s1 + a_aff * a_aff * s2) / nb;
-        T sigma = mu_aff / mu;
-        sigma = sigma * sigma * sigma;
-        const T sigmu = sigma * mu;
+        forward_sweep<NX, NU, T, false>(P, sm, ws);
+
+        // ================= F2: affine step lengths, mu_aff, corrector gradient pieces
+        T a_aff, mu_aff, sigmu;
+        {
+            T imax = T(0), acc1 = T(0), acc2 = T(0);
+            // stages are processed in batches: all loads of a batch are issued before any store,
+            // so a batch costs one memory round trip instead of one per stage
+            for (int k0 = 0; k0 < N; k0 += FB) {
+                BoxIn<T, FB> in;
+                load_box<NX, NU, T, FB, false>(in, ws, k0, N, N, lane);
+                MPCB_UNROLL
+                for (int u = 0; u < FB; u++) {
+                    if (!in.ok[u]) continue;
+                    T *wk = ws + (size_t)(k0 + u) * L::STAGE;
+                    const T tl = in.tl[u], tu = in.tu[u], ll = in.ll[u], lu = in.lu[u];
+                    const T itl = fast_rcp(tl), itu = fast_rcp(tu);
+                    const BoxStep<T> b = box_step(in.z[u], in.dza[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl, lu * tu, itl, itu);
+                    imax = fmax(imax, fmax(fmax(inv_ratio(b.dtl, itl), inv_ratio(b.dtu, itu)),
+                                           fmax(inv_ratio(b.dll, fast_rcp(ll)), inv_ratio(b.dlu, fast_rcp(lu)))));
+                    acc1 += ll * b.dtl + tl * b.dll + lu * b.dtu + tu * b.dlu;
+                    acc2 += b.dll * b.dtl + b.dlu * b.dtu;
+                    // corrector gradient: (dl_a dt_a - sigma mu)/t_l - (du_a dtu_a - sigma mu)/t_u = c1 - sigma mu * c2
+                    wk[L::O_C1 + lane] = b.dll * b.dtl * itl - b.dlu * b.dtu * itu;
+                    wk[L::O_C2 + lane] = itl - itu;
+                }
+            }
+            imax = warp_max(imax);
+            a_aff = (imax > T(1)) ? T(1) / imax : T(1);
+            const T s1 = warp_sum(acc1), s2 = warp_sum(acc2);
+            mu_aff = (mu * nb + a_aff * s1 + a_aff * a_aff * s2) / nb;
+            T sigma = mu_aff / mu;
+            sigma = sigma * sigma * sigma;
+            sigmu = sigma * mu;
+        }
+        warp_sync();
 
         // ================= S3: backward sweep for the corrector increment (delta form)
-        if (lane < NX) sm.sPv[lane] = T(0);
-        warp_sync();
-        for (int k = N - 1; k >= 0; k--) {
-            T *wk = ws + (size_t)k * L::STAGE;
-            load_BAt<NX, NU, T>(sm, wk);
-            T Lu[NU], invd[NU];
-            MPCB_UNROLL
-            for (int c = 0; c < NU; c++) {
-                Lu[c] = (lane < NZ) ? wk[L::O_LU + c * L::NZP + lane] : T(0);
-                invd[c] = wk[L::O_INVD + c];
-            }
-            const StageVar<T> sv = stage_var<NX, NU, T>(P, k, lane, Xi, Ui, yref, yps);
-            T l = T(0);
-            if (sv.hasb) {
-                const T z = wk[L::O_Z + lane], tl = wk[L::O_TL + lane], tu = wk[L::O_TU + lane];
-                const T ll = wk[L::O_LL + lane], lu = wk[L::O_LUP + lane];
-                const BoxStep<T> a = box_step(z, wk[L::O_DZA + lane], sv.lb, sv.ub, tl, tu, ll, lu, ll * tl, lu * tu);
-                l = (a.dll * a.dtl - sigmu) / tl - (a.dlu * a.dtu - sigmu) / tu;
-            }
-            warp_sync();
-            if (lane < NZ) {
-                for (int c = 0; c < NX; c++) l += sm.BAt[lane * L::LDB + c] * sm.sPv[c];
-            }
-            l = fwd_subst<NU, T>(l, Lu, invd, NZ);
-            warp_sync();
-            if (lane < NU) wk[L::O_LVEC + lane] += l;
-            else if (lane < NZ) { wk[L::O_PV + lane - NU] += l; sm.sPv[lane - NU] = l; }
-            warp_sync();
-        }
-
-        // ================= S4: forward sweep, full predictor-corrector step
-        T a_max, d1, d2;
-        forward_sweep<NX, NU, T, true>(P, sm, ws, Xi, Ui, yref, yps, sigmu, a_max, d1, d2);
-        const T alpha = fmin(T(1), fmax(T(0.995), T(1) - mu_aff) * a_max);
-
-        // ================= S5: take the step
-        T cmax = T(0), msum = T(0);
-        for (int k = 0; k <= N; k++) {
-            T *wk = ws + (size_t)k * L::STAGE;
-            const StageVar<T> sv = stage_var<NX, NU, T>(P, k, lane, Xi, Ui, yref, yps);
-            if (sv.var) {
-                const T z = wk[L::O_Z + lane], dz = wk[L::O_DZ + lane];
-                if (sv.hasb) {
-                    T tl = wk[L::O_TL + lane], tu = wk[L::O_TU + lane], ll = wk[L::O_LL + lane], lu = wk[L::O_LUP + lane];
-                    const BoxStep<T> a = box_step(z, wk[L::O_DZA + lane], sv.lb, sv.ub, tl, tu, ll, lu, ll * tl, lu * tu);
-                    const BoxStep<T> b = box_step(z, dz, sv.lb, sv.ub, tl, tu, ll, lu, ll * tl + a.dll * a.dtl - sigmu,
-                                                  lu * tu + a.dlu * a.dtu - sigmu);
-                    tl += alpha * b.dtl; tu += alpha * b.dtu; ll += alpha * b.dll; lu += alpha * b.dlu;
-                    wk[L::O_TL + lane] = tl; wk[L::O_TU + lane] = tu; wk[L::O_LL + lane] = ll; wk[L::O_LUP + lane] = lu;
-                    cmax = fmax(cmax, fmax(ll * tl, lu * tu));
-                    msum += ll * tl + lu * tu;
+        // record k: [BAt | Lu | invd | lvec] and [c1 c2]; pv_k is read-modify-written in global memory
+        {
+            constexpr int RUN1 = L::O_RB;
+            async_copy(sm.slot[(N - 1) & 1], ws + (size_t)(N - 1) * L::STAGE, RUN1);
+            async_copy(sm.slot[(N - 1) & 1] + L::O_C1, ws + (size_t)(N - 1) * L::STAGE + L::O_C1, 2 * L::NZP);
+            async_commit();
+            if (lane < NX) sm.cPv[lane] = T(0);
+            for (int k = N - 1; k >= 0; k--) {
+                T *wk = ws + (size_t)k * L::STAGE;
+                const T *s = sm.slot[k & 1];
+                const T pv_old = (lane >= NU && lane < NZ) ? wk[L::O_PV + lane - NU] : T(0);
+                if (k > 0) {
+                    T *nx = sm.slot[(k - 1) & 1];
+                    async_copy(nx, wk - L::STAGE, RUN1);
+                    async_copy(nx + L::O_C1, wk - L::STAGE + L::O_C1, 2 * L::NZP);
+                    async_commit();
+                    async_wait<1>();
+                } else {
+                    async_wait<0>();
                 }
-                wk[L::O_Z + lane] = z + alpha * dz;
+                warp_sync();
+                const int jr = lane < NZ ? lane : 0;
+                const VarKind vk = var_kind<NX, NU>(k, lane, N);
+                T l0 = vk.hasb ? s[L::O_C1 + lane] - sigmu * s[L::O_C2 + lane] : T(0), l1 = T(0);
+                MPCB_UNROLL
+                for (int c = 0; c + 1 < NX; c += 2) {
+                    l0 += s[L::O_BAT + jr * L::LDB + c] * sm.cPv[c];
+                    l1 += s[L::O_BAT + jr * L::LDB + c + 1] * sm.cPv[c + 1];
+                }
+                if (NX & 1) l0 += s[L::O_BAT + jr * L::LDB + NX - 1] * sm.cPv[NX - 1];
+                T Lu[NU], invd[NU];
+                MPCB_UNROLL
+                for (int c = 0; c < NU; c++) { Lu[c] = s[L::O_LU + c * L::NZP + jr]; invd[c] = s[L::O_INVD + c]; }
+                const T l = fwd_subst<NU, T>((lane < NZ) ? l0 + l1 : T(0), Lu, invd, NZ);
+                warp_sync();
+                if (lane < NU) wk[L::O_LVEC + lane] = s[L::O_LVEC + lane] + l;
+                else if (lane < NZ) { wk[L::O_PV + lane - NU] = pv_old + l; sm.cPv[lane - NU] = l; }
+                warp_sync();
             }
-            if (k >= 1 && lane < NX) wk[L::O_PI + lane] += alpha * wk[L::O_DPI + lane];
         }
-        comp = warp_max(cmax);
-        mu = warp_sum(msum) / nb;
+
+        // ================= S4: forward sweep, full predictor-corrector step (+ dpi)
+        forward_sweep<NX, NU, T, true>(P, sm, ws);
+
+        // ================= F4a: step length
+        T alpha;
+        {
+            T imax = T(0);
+            for (int k0 = 0; k0 < N; k0 += FB) {
+                BoxIn<T, FB> in;
+                load_box<NX, NU, T, FB, true>(in, ws, k0, N, N, lane);
+                MPCB_UNROLL
+                for (int u = 0; u < FB; u++) {
+                    if (!in.ok[u]) continue;
+                    const T tl = in.tl[u], tu = in.tu[u], ll = in.ll[u], lu = in.lu[u];
+                    const T itl = fast_rcp(tl), itu = fast_rcp(tu);
+                    const BoxStep<T> a = box_step(in.z[u], in.dza[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl, lu * tu, itl, itu);
+                    const BoxStep<T> b = box_step(in.z[u], in.dz[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl + a.dll * a.dtl - sigmu,
+                                                  lu * tu + a.dlu * a.dtu - sigmu, itl, itu);
+                    imax = fmax(imax, fmax(fmax(inv_ratio(b.dtl, itl), inv_ratio(b.dtu, itu)),
+                                           fmax(inv_ratio(b.dll, fast_rcp(ll)), inv_ratio(b.dlu, fast_rcp(lu)))));
+                }
+            }
+            imax = warp_max(imax);
+            // alpha = min(1, max(0.995, 1 - mu_aff) * alpha_max)
+            const T tau = fmax(T(0.995), T(1) - mu_aff);
+            alpha = (imax > tau) ? tau / imax : T(1);
+        }
+        // ================= F4b: take the step
+        {
+            T cmax = T(0), msum = T(0);
+            for (int k0 = 0; k0 <= N; k0 += FB) {
+                BoxIn<T, FB> in;
+                load_box<NX, NU, T, FB, true>(in, ws, k0, N + 1, N, lane);
+                T pi[FB], dpi[FB];
+                MPCB_UNROLL
+                for (int u = 0; u < FB; u++) {
+                    pi[u] = dpi[u] = T(0);
+                    if (k0 + u >= 1 && k0 + u <= N && lane < NX) {
+                        const T *wk = ws + (size_t)(k0 + u) * L::STAGE;
+                        pi[u] = wk[L::O_PI + lane];
+                        dpi[u] = wk[L::O_DPI + lane];
+                    }
+                }
+                MPCB_UNROLL
+                for (int u = 0; u < FB; u++) {
+                    const int k = k0 + u;
+                    if (k > N) continue;
+                    T *wk = ws + (size_t)k * L::STAGE;
+                    if (in.ok[u]) {
+                        T tl = in.tl[u], tu = in.tu[u], ll = in.ll[u], lu = in.lu[u];
+                        const T itl = fast_rcp(tl), itu = fast_rcp(tu);
+                        const BoxStep<T> a = box_step(in.z[u], in.dza[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl, lu * tu, itl, itu);
+                        const BoxStep<T> b = box_step(in.z[u], in.dz[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl + a.dll * a.dtl - sigmu,
+                                                      lu * tu + a.dlu * a.dtu - sigmu, itl, itu);
+                        tl += alpha * b.dtl; tu += alpha * b.dtu; ll += alpha * b.dll; lu += alpha * b.dlu;
+                        wk[L::O_TL + lane] = tl; wk[L::O_TU + lane] = tu; wk[L::O_LL + lane] = ll; wk[L::O_LUP + lane] = lu;
+                        cmax = fmax(cmax, fmax(ll * tl, lu * tu));
+                        msum += ll * tl + lu * tu;
+                    }
+                    if (in.var[u]) wk[L::O_Z + lane] = in.z[u] + alpha * in.dz[u];
+                    if (k >= 1 && lane < NX) wk[L::O_PI + lane] = pi[u] + alpha * dpi[u];
+                }
+            }
+            comp = warp_max(cmax);
+            mu = warp_sum(msum) / nb;
+        }
         est_g *= (T(1) - alpha);
         est_b *= (T(1) - alpha);
         est_d *= (T(1) - alpha);
@@ -507,6 +677,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
 
     // ---------------- RTI update: X += dx, U += du (full step)
     warp_sync();
+    MPCB_UNROLL4
     for (int k = 0; k <= N; k++) {
         const T *wk = ws + (size_t)k * L::STAGE;
         if (lane < NU) {

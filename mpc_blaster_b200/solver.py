@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference controller for the batched solve.
+
+``BlasterMPC`` takes the same positional arguments as the reference's
+``blasterModel(mass, J, l_x, l_y, N, Tf, c, Q, R, Q_t, blastThruster, statesBound,
+controlBound)`` (reference src/scripts/blastermodel.py:16) and exposes the per-step
+solve of src/scripts/simulation_blaster.py:56-105 as one batched call on torch CUDA
+tensors.  All arithmetic happens in libmpcb.so (hand-written CUDA, include/mpcb.h); torch
+only owns the device buffers and streams.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MPCB_PER_INSTANCE, MPCB_PER_STAGE, MPCB_SHARED, MpcbConfig
+
+
+def _diag(M, n, name):
+    M = np.asarray(M, dtype=np.float64)
+    if M.ndim == 1:
+        d = M
+    else:
+        d = np.diag(M)
+        if np.abs(M - np.diag(d)).max() != 0.0:
+            raise ValueError(f"{name} must be diagonal (the reference's weights are; acados_ocp_blasterModel.json cost.W)")
+    if d.shape[0] < n:
+        raise ValueError(f"{name} has {d.shape[0]} entries, need {n}")
+    return d[:n]
+
+
+class MpcbError(RuntimeError):
+    pass
+
+
+class BlasterMPC:
+    """B independent BLASTER controllers solved together on one GPU.
+
+    ``variant`` 17 = the reference's 17-state / 6-input model; 12 = QUAD12 (states 0..11,
+    inputs 0..3, gimbal frozen).  ``blastThruster`` is stored but, exactly as in the
+    reference (blastermodel.py:43), never used: the blast thrust is parameter p[24].
+    """
+
+    def __init__(self, mass, J, l_x, l_y, N, Tf, c, Q, R, Q_t, blastThruster, statesBound, controlBound, *,
+                 batch: int = 1, variant: int = 17, device=None, ws_batch: int = 0, ipm_max_iter: int = 60,
+                 ipm_mu0: float = 1e4, ipm_thr0: float = 10.0, tol_stat: float = 1e-6, tol_eq: float = 1e-8,
+                 tol_ineq: float = 1e-8, tol_comp: float = 1e-8, alpha_min: float = 1e-8):
+        if not torch.cuda.is_available():
+            raise MpcbError("BlasterMPC needs a CUDA device; this package has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nx, self.nu = (17, 6) if variant == 17 else (12, 4)
+        self.ny, self.N, self.batch = self.nx + self.nu, int(N), int(batch)
+        self.blastThruster = blastThruster
+        cfg = MpcbConfig()
+        cfg.variant, cfg.N, cfg.dt, cfg.mass = variant, int(N), float(Tf) / int(N), float(mass)
+        cfg.J[:] = np.asarray(J, dtype=np.float64).reshape(9)
+        cfg.l_x, cfg.l_y, cfg.c = float(l_x), float(l_y), float(c)
+        sb = np.asarray(statesBound, dtype=np.float64)
+        cb = np.asarray(controlBound, dtype=np.float64)
+        for name, vals, n in (("Q", _diag(Q, self.nx, "Q"), self.nx), ("R", _diag(R, self.nu, "R"), self.nu),
+                              ("Qt", _diag(Q_t, self.nx, "Q_t"), self.nx), ("lbx", sb[0], self.nx), ("ubx", sb[1], self.nx),
+                              ("lbu", cb[0], self.nu), ("ubu", cb[1], self.nu)):
+            arr = getattr(cfg, name)
+            for i in range(n):
+                arr[i] = float(vals[i])
+        cfg.ipm_max_iter, cfg.ipm_mu0, cfg.ipm_thr0 = ipm_max_iter, ipm_mu0, ipm_thr0
+        cfg.tol_stat, cfg.tol_eq, cfg.tol_ineq, cfg.tol_comp, cfg.alpha_min = tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min
+        cfg.max_batch, cfg.ws_batch, cfg.device = self.batch, ws_batch, self.device.index
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        if self.lib.mpcb_create(C.byref(cfg), C.byref(self._h)) != 0:
+            raise MpcbError("mpcb_create: " + self.lib.mpcb_last_error(None).decode())
+        self._yref = None
+
+    # ------------------------------------------------------------------ helpers
+    @classmethod
+    def canonical(cls, N: int = 20, batch: int = 1, variant: int = 17, **kw):
+        """Constants of reference simulation_blaster.py:12-30 with dt = 1/30 s."""
+        Q = np.diag([1e3] * 6 + [5.0] * 3 + [10.0] * 3 + [1e-2] * 2 + [1e3] * 3)
+        R = np.diag([5e-2] * 4 + [1e-5] * 2)
+        sb = np.array([[-1.5, -1.5, 0, -0.174532925, -0.174532925, -0.349066, -1.0, -1.0, -1.0, -0.0872665, -0.0872665,
+                        -0.0872665, -0.174532925, -0.523599, -1.5, -1.5, -2.5],
+                       [1.5, 1.5, 5.0, 0.174532925, 0.174532925, 0.349066, 1.0, 1.0, 1.0, 0.0872665, 0.0872665, 0.0872665,
+                        1.22173, 0.523599, 1.5, 1.5, 2.5]])
+        cb = np.array([[0, 0, 0, 0, -0.0872665, -0.0872665], [65, 65, 65, 65, 0.0872665, 0.0872665]], dtype=np.float64)
+        J = np.diag([0.50781, 0.47314, 0.72975])
+        return cls(9.0, J, 0.3434, 0.3475, N, N / 30.0, 0.03, Q, R, 10 * Q, 2.2 * 9.81, sb, cb, batch=batch,
+                   variant=variant, **kw)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.lib.mpcb_destroy(h)
+            self._h = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MpcbError(f"{what}: " + self.lib.mpcb_last_error(self._h).decode())
+
+    def _t(self, a, shape_tail, name):
+        """float64 contiguous CUDA tensor on this solver's device."""
+        t = torch.as_tensor(a, dtype=torch.float64, device=self.device).contiguous()
+        if tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+            raise ValueError(f"{name}: expected trailing shape {shape_tail}, got {tuple(t.shape)}")
+        return t
+
+    def _mode(self, t, B, per_stage_rows, width, name):
+        if t.dim() == 1:
+            return MPCB_SHARED
+        if t.dim() == 2 and t.shape == (B, width):
+            return MPCB_PER_INSTANCE
+        if t.dim() == 3 and t.shape == (B, per_stage_rows, width):
+            return MPCB_PER_STAGE
+        raise ValueError(f"{name}: shape {tuple(t.shape)} is none of [{width}], [B,{width}], [B,{per_stage_rows},{width}]")
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    # ------------------------------------------------------------------ API
+    def reset(self, x_init=None, u_init=None, B: int | None = None):
+        """Set the stored SQP iterate (zeros by default, acados' initial iterate);
+        x_init[B,nx] is copied to every stage, u_init[nu] or [B,nu] likewise."""
+        B = self.batch if B is None else B
+        with torch.cuda.device(self.device):
+            xi = None if x_init is None else self._t(x_init, (self.nx,), "x_init").reshape(B, self.nx)
+            ui = None if u_init is None else self._t(u_init, (self.nu,), "u_init")
+            per = int(ui is not None and ui.dim() == 2)
+            self._check(self.lib.mpcb_reset(self._h, self._p(xi), self._p(ui), per, B, self._stream()), "mpcb_reset")
+
+    def solve(self, x0, yref, p=None, want_traj: bool = True):
+        """One SQP-RTI iteration for every instance: returns (u0[B,nu], X[B,N+1,nx],
+        U[B,N,nu], status[B] int32).  yref: [ny] | [B,ny] | [B,N+1,ny]; p: None | [25] |
+        [B,25] | [B,N,25].  The iterate is kept in the handle for the next call (un-shifted
+        warm start, as the reference's loop does)."""
+        with torch.cuda.device(self.device):
+            x0 = self._t(x0, (self.nx,), "x0")
+            B = x0.shape[0] if x0.dim() == 2 else 1
+            x0 = x0.reshape(B, self.nx)
+            yref = self._t(yref, (self.ny,), "yref")
+            ymode = self._mode(yref, B, self.N + 1, self.ny, "yref")
+            pmode, pt = MPCB_SHARED, None
+            if p is not None:
+                pt = self._t(p, (25,), "p")
+                pmode = self._mode(pt, B, self.N, 25, "p")
+            u0 = torch.empty((B, self.nu), dtype=torch.float64, device=self.device)
+            X = torch.empty((B, self.N + 1, self.nx), dtype=torch.float64, device=self.device) if want_traj else None
+            U = torch.empty((B, self.N, self.nu), dtype=torch.float64, device=self.device) if want_traj else None
+            status = torch.empty((B,), dtype=torch.int32, device=self.device)
+            self.iters = torch.empty((B,), dtype=torch.int32, device=self.device)
+            self._check(self.lib.mpcb_solve(self._h, self._p(x0), self._p(yref), ymode, self._p(pt), pmode, self._p(u0),
+                                            self._p(X), self._p(U), self._p(status), self._p(self.iters), B, self._stream()),
+                        "mpcb_solve")
+            self._yref = yref
+        return u0, X, U, status
+
+    def solve_host(self, x0, yref, p=None, want_traj: bool = False):
+        """Same through ``mpcb_solve_host``: NumPy in, NumPy out, copies inside the call."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        B = x0.shape[0]
+        yref = np.ascontiguousarray(yref, dtype=np.float64)
+        ymode = {1: MPCB_SHARED, 2: MPCB_PER_INSTANCE, 3: MPCB_PER_STAGE}[yref.ndim]
+        pmode, pp = MPCB_SHARED, None
+        if p is not None:
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            pmode, pp = {1: MPCB_SHARED, 2: MPCB_PER_INSTANCE, 3: MPCB_PER_STAGE}[p.ndim], p.ctypes.data
+        u0 = np.empty((B, self.nu))
+        X = np.empty((B, self.N + 1, self.nx)) if want_traj else None
+        U = np.empty((B, self.N, self.nu)) if want_traj else None
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        self._check(self.lib.mpcb_solve_host(self._h, x0.ctypes.data, yref.ctypes.data, ymode, pp, pmode, u0.ctypes.data,
+                                             None if X is None else X.ctypes.data, None if U is None else U.ctypes.data,
+                                             status.ctypes.data, iters.ctypes.data, B), "mpcb_solve_host")
+        self.iters_host = iters
+        return u0, X, U, status
+
+    def step_plant(self, x, u, p=None):
+        """x+ = RK4(x, u, p) over dt (the reference's AcadosSimSolver)."""
+        with torch.cuda.device(self.device):
+            x = self._t(x, (self.nx,), "x")
+            B = x.shape[0] if x.dim() == 2 else 1
+            x = x.reshape(B, self.nx)
+            u = self._t(u, (self.nu,), "u").reshape(B, self.nu)
+            pmode, pt = MPCB_SHARED, None
+            if p is not None:
+                pt = self._t(p, (25,), "p")
+                pmode = MPCB_SHARED if pt.dim() == 1 else MPCB_PER_INSTANCE
+            xn = torch.empty_like(x)
+            self._check(self.lib.mpcb_plant_step(self._h, self._p(x), self._p(u), self._p(pt), pmode, self._p(xn), B,
+                                                 self._stream()), "mpcb_plant_step")
+        return xn
+
+    def closed_loop(self, x0, yref, p=None, steps: int = 1):
+        """``steps`` control steps on the device: returns (x_final[B,nx], u_last[B,nu],
+        n_fail[B], iters_sum[B])."""
+        with torch.cuda.device(self.device):
+            x = self._t(x0, (self.nx,), "x0").reshape(-1, self.nx).clone()
+            B = x.shape[0]
+            yref = self._t(yref, (self.ny,), "yref")
+            ymode = self._mode(yref, B, self.N + 1, self.ny, "yref")
+            pmode, pt = MPCB_SHARED, None
+            if p is not None:
+                pt = self._t(p, (25,), "p")
+                pmode = MPCB_SHARED if pt.dim() == 1 else MPCB_PER_INSTANCE
+            u_last = torch.empty((B, self.nu), dtype=torch.float64, device=self.device)
+            n_fail = torch.empty((B,), dtype=torch.int32, device=self.device)
+            iters = torch.empty((B,), dtype=torch.int32, device=self.device)
+            self._check(self.lib.mpcb_closed_loop(self._h, self._p(x), self._p(yref), ymode, self._p(pt), pmode, int(steps),
+                                                  self._p(u_last), self._p(n_fail), self._p(iters), B, self._stream()),
+                        "mpcb_closed_loop")
+            self._yref = yref
+        return x, u_last, n_fail, iters
+
+    def cost(self, yref=None, B: int | None = None):
+        """Objective at the stored iterate (acados ``get_cost()``)."""
+        with torch.cuda.device(self.device):
+            yref = self._yref if yref is None else self._t(yref, (self.ny,), "yref")
+            B = self.batch if B is None else B
+            ymode = self._mode(yref, B, self.N + 1, self.ny, "yref")
+            out = torch.empty((B,), dtype=torch.float64, device=self.device)
+            self._check(self.lib.mpcb_cost(self._h, self._p(yref), ymode, self._p(out), B, self._stream()), "mpcb_cost")
+        return out
+
+    def iterate(self, B: int | None = None):
+        B = self.batch if B is None else B
+        with torch.cuda.device(self.device):
+            X = torch.empty((B, self.N + 1, self.nx), dtype=torch.float64, device=self.device)
+            U = torch.empty((B, self.N, self.nu), dtype=torch.float64, device=self.device)
+            self._check(self.lib.mpcb_get_iterate(self._h, self._p(X), self._p(U), B, self._stream()), "mpcb_get_iterate")
+        return X, U
+
+    def set_iterate(self, X=None, U=None):
+        with torch.cuda.device(self.device):
+            Xt = None if X is None else self._t(X, (self.N + 1, self.nx), "X")
+            Ut = None if U is None else self._t(U, (self.N, self.nu), "U")
+            B = (Xt if Xt is not None else Ut).shape[0]
+            self._check(self.lib.mpcb_set_iterate(self._h, self._p(Xt), self._p(Ut), B, self._stream()), "mpcb_set_iterate")
+
+    def linearize(self, p=None, B: int | None = None):
+        """Test hook: (A[B,N,nx,nx], B[B,N,nx,nu], b[B,N,nx]) of the stored iterate."""
+        B = self.batch if B is None else B
+        nz = self.nx + self.nu
+        with torch.cuda.device(self.device):
+            pmode, pt = MPCB_SHARED, None
+            if p is not None:
+                pt = self._t(p, (25,), "p")
+                pmode = self._mode(pt, B, self.N, 25, "p")
+            BAt = torch.empty((B, self.N, nz, self.nx), dtype=torch.float64, device=self.device)
+            b = torch.empty((B, self.N, self.nx), dtype=torch.float64, device=self.device)
+            self._check(self.lib.mpcb_debug_linearize(self._h, self._p(pt), pmode, self._p(BAt), self._p(b), B,
+                                                      self._stream()), "mpcb_debug_linearize")
+        return BAt[:, :, self.nu:, :].transpose(2, 3), BAt[:, :, :self.nu, :].transpose(2, 3), b
+
+    def command_map(self, x, u0):
+        """Attitude quaternion [w,x,y,z] and normalised thrust set-point
+        (reference mavros_blaster_sim.py:27-30,91-100)."""
+        with torch.cuda.device(self.device):
+            x = self._t(x, (self.nx,), "x").reshape(-1, self.nx)
+            u0 = self._t(u0, (self.nu,), "u0").reshape(-1, self.nu)
+            B = x.shape[0]
+            quat = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+            thrust = torch.empty((B,), dtype=torch.float64, device=self.device)
+            self._check(self.lib.mpcb_command_map(self._h, self._p(x), self._p(u0), self._p(quat), self._p(thrust), B,
+                                                  self._stream()), "mpcb_command_map")
+        return quat, thrust
+
+    def profile(self, enable: bool = True):
+        self._check(self.lib.mpcb_profile(self._h, int(enable)), "mpcb_profile")
+
+    def last_kernel_ms(self):
+        """(rollout kernel ms, QP kernel ms) of the last solve; needs profile(True)."""
+        a, b = C.c_float(0), C.c_float(0)
+        self._check(self.lib.mpcb_last_kernel_ms(self._h, C.byref(a), C.byref(b)), "mpcb_last_kernel_ms")
+        return a.value, b.value
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0)
+        self._check(self.lib.mpcb_fp64_peak(self.device.index, C.byref(v)), "mpcb_fp64_peak")
+        return v.value
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.mpcb_kernel_launches())

@@ -421,9 +421,10 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
     CUDA path, but every Newton system is solved on the *dense* KKT matrix with
     pivoted LU.
 
-    The stationarity residual enters the stopping test through its exact-arithmetic
-    value |r_g0| * prod(1 - alpha_j) (r_g is affine in the iterate and everything takes
-    the same step); see DESIGN.md "stopping test"."""
+    The linear residuals (stationarity, dynamics, bound-slack) enter the stopping test
+    through their exact-arithmetic values |r_0| * prod(1 - alpha_j): they are affine in
+    the iterate and everything takes the same step (DESIGN.md "stopping test").  ``res``
+    also carries the explicitly evaluated norms for the tests."""
     n, m = g.size, c.size
     il, iu = np.isfinite(lb), np.isfinite(ub)
     lbf = np.where(il, lb, 0.0)
@@ -449,10 +450,11 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
         r_du = np.where(iu, ubf - z - tu, 0.0)
         mu = (ll @ tl + lu @ tu) / nb if nb else 0.0
         comp = max(np.max(ll * tl * il, initial=0.0), np.max(lu * tu * iu, initial=0.0))
+        explicit = (np.abs(r_g).max(), np.abs(r_b).max(initial=0.0),
+                    max(np.abs(r_dl).max(initial=0.0), np.abs(r_du).max(initial=0.0)))
         if rg_est is None:
-            rg_est = np.abs(r_g).max()
-        res = (rg_est, np.abs(r_b).max(initial=0.0),
-               max(np.abs(r_dl).max(initial=0.0), np.abs(r_du).max(initial=0.0)), comp, np.abs(r_g).max())
+            rg_est, rb_est, rd_est = explicit
+        res = (rg_est, rb_est, rd_est, comp) + explicit
         if not np.isfinite(res[0] + res[1] + mu):
             status = 1
             break
@@ -502,10 +504,14 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
         ll = ll + a * dll
         lu = lu + a * dlu
         rg_est *= (1.0 - a)
+        rb_est *= (1.0 - a)
+        rd_est *= (1.0 - a)
         if not (a >= alpha_min):
             status = 3 if a == a else 1
             it += 1
             break
+    if status == 2:
+        it = max_iter
     return IPMResult(z, pi, np.where(il, ll, 0.0), np.where(iu, lu, 0.0), it, status, res)
 
 

@@ -336,7 +336,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
     }
     for (size_t i = 0; i < (size_t)(N + 1) * NX; i++) w->pi[i] = 0.0;
     int status = 2, it;
-    double rg_est = 0.0;
+    double rg_est = 0.0, rb_est = 0.0, rd_est = 0.0;
     for (it = 0; it < P->ipm_max_iter; it++) {
         /* residuals */
         double res_g = 0, res_b = 0, res_d = 0, comp = 0, mu = 0;
@@ -374,13 +374,20 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
                 }
         }
         if (nb) mu /= nb;
-        if (it == 0) rg_est = res_g;
-        if (P->rg_mode == 2) res_g = rg_est;
+        if (it == 0) { rg_est = res_g; rb_est = res_b; rd_est = res_d; }
+        /* the three linear residuals are affine in the iterate and everything takes the same
+         * step, so each shrinks by exactly (1-alpha); the stopping test uses those values */
+        if (P->rg_mode == 2) { res_g = rg_est; res_b = rb_est; res_d = rd_est; }
         if (getenv("ORC_DEBUG")) fprintf(stderr, "it %d res_g %.3e res_b %.3e res_d %.3e comp %.3e mu %.3e\n", it, res_g, res_b, res_d, comp, mu);
         if (!(res_g == res_g) || !(res_b == res_b) || !(mu == mu)) { status = 1; break; }
         if (res_g <= P->tol_stat && res_b <= P->tol_eq && res_d <= P->tol_ineq && comp <= P->tol_comp) { status = 0; break; }
         /* factorise with barrier diagonal */
         for (size_t i = 0; i < n; i++) w->Hd[i] = w->H0[i] + w->ll[i] / w->tl[i] + w->lu[i] / w->tu[i];
+        if (getenv("ORC_DEBUG")) {
+            double gmax = 0, gxmax = 0;
+            for (size_t i = 0; i < n; i++) { double gm = w->Hd[i] - w->H0[i]; if (gm > gmax) gmax = gm; if ((int)(i % NZ) >= NU && gm > gxmax) gxmax = gm; }
+            fprintf(stderr, "   barrier max %.3e  (states %.3e)\n", gmax, gxmax);
+        }
         if (SFX(ric_factor)(P, w, N)) { status = 4; break; }
         double alpha = 1.0;
         if (nb) {
@@ -418,7 +425,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
          * r_g <- (1-alpha) r_g exactly; evaluating it explicitly needs the multipliers of
          * numerically pinned states, whose absolute accuracy degrades like eps*lam/t. */
         if (P->rg_mode == 0) for (size_t i = 0; i < n; i++) w->rg[i] *= (1.0 - alpha);
-        rg_est *= (1.0 - alpha);
+        rg_est *= (1.0 - alpha); rb_est *= (1.0 - alpha); rd_est *= (1.0 - alpha);
         if (!(alpha >= P->alpha_min)) { status = (alpha == alpha) ? 3 : 1; it++; break; } /* [upstream D9] 3 = min step */
     }
     *iters_out = it;

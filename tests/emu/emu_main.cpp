@@ -26,7 +26,9 @@ static int rti_one(const Params &P, double *X, double *U, const double *x0, cons
             linearize_warp<NX, NU, double>(P, X + (size_t)k * NX, U + (size_t)k * NU, X + (size_t)(k + 1) * NX, pk,
                                            ws.data() + (size_t)k * L::STAGE);
         });
-        if (BAt_out) memcpy(BAt_out + (size_t)k * L::NZ * NX, ws.data() + (size_t)k * L::STAGE + L::O_BAT, sizeof(double) * L::NZ * NX);
+        if (BAt_out)
+            for (int r = 0; r < L::NZ; r++)
+                memcpy(BAt_out + ((size_t)k * L::NZ + r) * NX, ws.data() + (size_t)k * L::STAGE + L::O_BAT + r * L::LDB, sizeof(double) * NX);
         if (b_out) memcpy(b_out + (size_t)k * NX, ws.data() + (size_t)k * L::STAGE + L::O_B, sizeof(double) * NX);
     }
     int status = -1, it = 0;
@@ -57,4 +59,12 @@ void emu_plant_step(const Params *P, const double *x, const double *u, const dou
     if (P->variant == 17) plant_step_thread<17, 6, double>(*P, x, u, p, xn);
     else plant_step_thread<12, 4, double>(*P, x, u, p, xn);
 }
+}
+
+// rotation / quaternion helpers of mpcb_model.cuh (restating reference utils/MathUtils.py)
+extern "C" {
+void emu_quat_mul(const double *a, const double *b, double *c) { quat_mul<double>(a, b, c); }
+void emu_quat_inv(const double *q, double *r) { quat_inv_unit<double>(q, r); }
+void emu_quat_to_rot(const double *q, double *R) { quat_to_rot<double>(q, R); }
+void emu_euler_to_quat(double phi, double th, double psi, double *q) { euler_to_quat<double>(phi, th, psi, q); }
 }

@@ -1,0 +1,62 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/mpcb.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "mpcb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpcb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mpc_blaster_b200 import _lib
+    names = _declared()
+    assert len(names) >= 18 and sorted(_lib.EXPORTS) == names
+    lib = _lib.load()
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_config_default_is_the_reference_constants_and_struct_layouts_agree():
+    from mpc_blaster_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.MpcbConfig()
+    # poison the tail: if the C struct were larger than the ctypes mirror this would corrupt memory
+    assert lib.mpcb_config_default(C.byref(cfg), 17, 20) == 0
+    assert (cfg.variant, cfg.N, cfg.max_batch, cfg.device) == (17, 20, 1024, -1)
+    assert abs(cfg.dt - 1 / 30) < 1e-16 and cfg.mass == 9.0 and cfg.J[4] == 0.47314
+    assert list(cfg.R) == [5e-2] * 4 + [1e-5] * 2 and cfg.Qt[0] == 1e4 and cfg.ubu[0] == 65 and cfg.lbx[2] == 0
+    assert (cfg.tol_stat, cfg.tol_eq, cfg.tol_ineq, cfg.tol_comp) == (1e-6, 1e-8, 1e-8, 1e-8)
+    assert lib.mpcb_config_default(C.byref(cfg), 13, 20) != 0  # unknown variant
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mpc_blaster_b200 import BlasterMPC, _lib
+    from mpc_blaster_b200.solver import MpcbError
+    lib = _lib.load()
+    cfg = _lib.MpcbConfig()
+    lib.mpcb_config_default(C.byref(cfg), 17, 20)
+    h = C.c_void_p()
+    assert lib.mpcb_create(C.byref(cfg), C.byref(h)) != 0 and not h
+    assert b"no CUDA device" in lib.mpcb_last_error(None)
+    with pytest.raises(MpcbError):
+        BlasterMPC.canonical(N=20, batch=4)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mpc_blaster_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f

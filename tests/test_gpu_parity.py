@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle.
+
+Tolerances (BASELINE.json north_star): FP64 |du|,|dx| <= 1e-6 at matched KKT tolerance.
+Both sides run the same Mehrotra iteration with the same stopping test (HPIPM's default
+tolerances), so they are expected to agree to ~1e-9; the bound asserted is 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from mpc_blaster_b200 import scenarios as sc
+from oracle import blaster_oracle as bo
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6  # FP64 parity bound of north_star
+
+
+def _mpc(N, B, variant=17, **kw):
+    from mpc_blaster_b200 import BlasterMPC
+    return BlasterMPC.canonical(N=N, batch=B, variant=variant, **kw)
+
+
+@pytest.mark.parametrize("variant", [17, 12])
+def test_linearize_matches_oracle(cuda_device, variant):
+    P = bo.canonical_problem(8, variant)
+    B = 16
+    rng = np.random.default_rng(5)
+    x0, _ = sc.random_setpoints(B, seed=11, nx=P.nx, nu=P.nu)
+    mpc = _mpc(8, B, variant)
+    X = np.repeat(x0[:, None, :], P.N + 1, axis=1) + 0.01 * rng.standard_normal((B, P.N + 1, P.nx))
+    U = np.tile(sc.hover_trim(P.nu), (B, P.N, 1)) + rng.uniform(-2, 2, (B, P.N, P.nu)) * np.array([1, 1, 1, 1, .01, .01])[:P.nu]
+    p = rng.standard_normal((B, P.N, 25)) * 0.1
+    p[..., 24] = 2.2 * 9.81 + rng.uniform(-1, 1, (B, P.N))
+    mpc.set_iterate(X, U)
+    A, Bm, b = (t.cpu().numpy() for t in mpc.linearize(p))
+    for i in range(B):
+        for k in range(P.N):
+            xn, Ao, Bo = bo.rk4_sens(X[i, k], U[i, k], p[i, k], P)
+            assert np.abs(A[i, k] - Ao).max() < 1e-12
+            assert np.abs(Bm[i, k] - Bo).max() < 1e-12
+            assert np.abs(b[i, k] - (xn - X[i, k + 1])).max() < 1e-12
+
+
+def test_plant_step_and_cost(cuda_device):
+    P = bo.canonical_problem(10)
+    B = 64
+    x0, yref = sc.random_setpoints(B, seed=3)
+    rng = np.random.default_rng(0)
+    u = np.tile(sc.hover_trim(), (B, 1)) + rng.uniform(-3, 3, (B, 6)) * np.array([1, 1, 1, 1, .01, .01])
+    p = rng.standard_normal((B, 25)) * 0.1
+    mpc = _mpc(10, B)
+    xn = mpc.step_plant(x0, u, p).cpu().numpy()
+    ref = np.stack([bo.plant_step(x0[i], u[i], p[i], P) for i in range(B)])
+    assert np.abs(xn - ref).max() < 1e-13
+    mpc.reset(x0, sc.hover_trim())
+    c = mpc.cost(yref).cpu().numpy()
+    X = np.repeat(x0[:, None], P.N + 1, axis=1)
+    U = np.tile(sc.hover_trim(), (P.N, 1))
+    ref = np.array([bo.stage_cost(X[i], U, yref[i], P) for i in range(B)])
+    assert np.allclose(c, ref, rtol=1e-13, atol=0)
+
+
+def test_hover_to_setpoint_closed_loop_vs_numpy_oracle(cuda_device):
+    """Config 1 (simulation_blaster.py:47-48), zero initial iterate, 12 closed-loop steps against
+    the dense-KKT NumPy oracle; the reference QP here has thrust, vz and swivel-rate bounds active
+    (SURVEY appendix C).
+
+    Before every step the solver is seeded with the oracle's iterate, so both linearise about the
+    same point and the full (X, U) must agree to the 1e-6 parity bound.  (Two free-running
+    closed loops are not comparable at 1e-6: the swivel-rate inputs have curvature dt*1e-5 =
+    3.3e-7, so they are determined only up to (KKT tolerance)/(3.3e-7) per step and the iterates
+    drift apart chaotically -- see DESIGN.md "what 1e-6 parity means".)"""
+    P = bo.canonical_problem(20)
+    x0, yref = bo.canonical_x0_yref()
+    mpc = _mpc(20, 1)
+    ctl = bo.RTIOracle(P)
+    x = x0.copy()
+    for step in range(12):
+        mpc.set_iterate(ctl.X[None], ctl.U[None])
+        u0, X, U, st = mpc.solve(x[None], yref)
+        uo, Xo, Uo, sto = ctl.solve(x, yref)
+        assert int(st[0]) == sto == 0
+        assert int(mpc.iters[0]) == ctl.last[1].iters
+        assert np.abs(U[0].cpu().numpy() - Uo).max() < TOL
+        assert np.abs(X[0].cpu().numpy() - Xo).max() < TOL
+        assert np.abs(u0[0].cpu().numpy() - uo).max() < TOL
+        if step == 0:
+            assert np.allclose(uo[:4], 65.0, atol=1e-6)  # all four rotors saturate on the first step
+        x = bo.plant_step(x, uo, bo.default_params(), P)
+
+
+@pytest.mark.parametrize("variant,N", [(17, 20), (12, 20), (17, 40)])
+def test_batch_solve_matches_c_oracle(cuda_device, variant, N):
+    """Config 2 (B=1024 random set-points) and the N=40 / QUAD12 instantiations, two RTI
+    steps (cold iterate, then warm), against the C oracle on identical inputs."""
+    B = 1024 if N == 20 else 256
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.random_setpoints(B, seed=1234, nx=P.nx, nu=P.nu)
+    mpc = _mpc(N, B, variant)
+    orc = co.BatchRTI(P, B)
+    trim = sc.hover_trim(P.nu)
+    mpc.reset(x0, trim)
+    orc.reset(x0, trim)
+    x = x0
+    for step in range(2):
+        u0, X, U, st = mpc.solve(x, yref)
+        uo, Xo, Uo, sto = orc.solve(x, yref)
+        st = st.cpu().numpy()
+        assert (st == sto).all()
+        ok = sto == 0
+        assert ok.mean() > 0.99
+        assert (mpc.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
+        assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL
+        assert np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+        assert np.abs(u0.cpu().numpy()[ok] - uo[ok]).max() < TOL
+        x = co.plant_step(P, x, uo)
+
+
+def test_tracking_per_stage_yref_and_params(cuda_device):
+    """Config 3 flavour: per-stage yref[B,N+1,ny] (figure-eight) and per-stage p[B,N,25]."""
+    N, B = 40, 128
+    P = bo.canonical_problem(N)
+    x0, yref = sc.lemniscate_tracking(B, N)
+    rng = np.random.default_rng(7)
+    p = np.zeros((B, N, 25))
+    p[..., :24] = 0.05 * rng.standard_normal((B, 1, 24))
+    p[..., 24] = 2.2 * 9.81
+    mpc = _mpc(N, B)
+    orc = co.BatchRTI(P, B)
+    mpc.reset(x0, sc.hover_trim())
+    orc.reset(x0, sc.hover_trim())
+    u0, X, U, st = mpc.solve(x0, yref, p)
+    uo, Xo, Uo, sto = orc.solve(x0, yref, p)
+    assert (st.cpu().numpy() == sto).all()
+    ok = sto == 0
+    assert ok.mean() > 0.95
+    assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL
+    assert np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+
+
+def test_solution_is_qp_optimal_kkt_certificate(cuda_device):
+    """Solver-independent check: the GPU's step satisfies the KKT conditions of the QP the
+    NumPy oracle builds, with multipliers recovered by least squares on the active set."""
+    P = bo.canonical_problem(20)
+    B = 8
+    x0, yref = sc.random_setpoints(B, seed=99)
+    mpc = _mpc(20, B, tol_comp=1e-11)
+    trim = sc.hover_trim()
+    mpc.reset(x0, trim)
+    X0 = np.repeat(x0[:, None], P.N + 1, axis=1)
+    U0 = np.tile(trim, (B, P.N, 1))
+    u0, X, U, st = mpc.solve(x0, yref)
+    X, U = X.cpu().numpy(), U.cpu().numpy()
+    for i in range(B):
+        assert int(st[i]) == 0
+        qp = bo.build_qp(X0[i], U0[i], x0[i], yref[i], None, P)
+        H, g, C, c, lb, ub = bo.qp_to_dense(qp)
+        z = np.hstack([np.hstack([U[i, k] - U0[i, k], X[i, k + 1] - X0[i, k + 1]]) for k in range(P.N)])
+        pi, ll, lu = bo.multipliers_from_primal(H, g, C, lb, ub, z, act_tol=1e-7)
+        cert = bo.kkt_certificate(H, g, C, c, lb, ub, z, pi, ll, lu)
+        assert cert["eq"] < 1e-9 and cert["viol"] < 1e-9
+        assert cert["stat"] < 1e-5 * max(1.0, np.abs(g).max())
+        assert cert["neg"] < 1e-6 * max(1.0, np.abs(g).max())
+
+
+def test_solve_host_equals_device_path(cuda_device):
+    B, N = 96, 20
+    x0, yref = sc.random_setpoints(B, seed=21)
+    a = _mpc(N, B)
+    b = _mpc(N, B)
+    u0, X, U, st = a.solve(x0, yref)
+    uh, Xh, Uh, sth = b.solve_host(x0, yref, want_traj=True)
+    assert np.array_equal(u0.cpu().numpy(), uh) and np.array_equal(X.cpu().numpy(), Xh)
+    assert np.array_equal(U.cpu().numpy(), Uh) and np.array_equal(st.cpu().numpy(), sth)
+
+
+def test_closed_loop_on_device_matches_stepwise(cuda_device):
+    B, N, steps = 64, 20, 5
+    x0, yref = sc.random_setpoints(B, seed=4)
+    a = _mpc(N, B)
+    b = _mpc(N, B)
+    a.reset(x0, sc.hover_trim())
+    b.reset(x0, sc.hover_trim())
+    xa, ua, nfail, its = a.closed_loop(x0, yref, steps=steps)
+    x = torch.as_tensor(x0, device="cuda")
+    tot = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for _ in range(steps):
+        u0, _, _, st = b.solve(x, yref, want_traj=False)
+        tot += b.iters
+        x = b.step_plant(x, u0)
+    assert torch.equal(xa, x) and torch.equal(ua, u0) and torch.equal(its, tot)
+    assert int(nfail.sum()) == 0
+
+
+def test_chunked_workspace_is_bit_identical(cuda_device):
+    """The host scheduler's chunking (ws_batch < B) must not change any result."""
+    B, N = 200, 20
+    x0, yref = sc.random_setpoints(B, seed=8)
+    a = _mpc(N, B)
+    b = _mpc(N, B, ws_batch=64)
+    ra = a.solve(x0, yref)
+    rb = b.solve(x0, yref)
+    for s, t in zip(ra, rb):
+        assert torch.equal(s, t)
+
+
+def test_infeasible_instance_reports_status_and_does_not_poison_others(cuda_device):
+    B, N = 32, 20
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(B, seed=15)
+    x0[5, 6] = 3.0  # vx far outside its +-1 bound: the stage-1 state bound cannot be met
+    mpc = _mpc(N, B)
+    orc = co.BatchRTI(P, B)
+    mpc.reset(x0, sc.hover_trim())
+    orc.reset(x0, sc.hover_trim())
+    u0, X, U, st = mpc.solve(x0, yref)
+    uo, Xo, Uo, sto = orc.solve(x0, yref)
+    st = st.cpu().numpy()
+    assert st[5] != 0 and (st == sto).all()
+    ok = sto == 0
+    assert ok.sum() >= B - 2
+    assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL
+
+
+def test_acados_shaped_shim_runs_the_reference_loop_body(cuda_device):
+    """The body of simulation_blaster.py:56-105 (minus printing) against the shim."""
+    from mpc_blaster_b200 import blasterModel
+    N, Tf, nx, nu = 20, 20 / 30.0, 17, 6
+    P = bo.canonical_problem(N)
+    Q = np.diag(P.Q)
+    R = np.diag(P.R)
+    b = blasterModel(P.mass, P.J, P.l_x, P.l_y, N, Tf, P.c, Q, R, 10 * Q, 2.2 * 9.81, np.array([P.lbx, P.ubx]),
+                     np.array([P.lbu, P.ubu]))
+    b.generateModel()
+    integrator, ocp_solver = b.generateController()
+    J_mot, J_eul, J_pos = np.zeros((3, 2)), np.zeros((3, 3)), np.zeros((3, 3))
+    blastThruster = 2.2 * 9.81
+    x0, yref = bo.canonical_x0_yref()
+    ctl = bo.RTIOracle(P)
+    xcurrent = x0
+    for i in range(4):
+        ocp_solver.set(0, "lbx", xcurrent)
+        ocp_solver.set(0, "ubx", xcurrent)
+        ocp_solver.cost_set(0, 'yref', yref)
+        for k in range(N):
+            params = np.vstack((np.reshape(J_mot, (J_mot.size, 1), order='F'), np.reshape(J_eul, (J_eul.size, 1), order='F'),
+                                np.reshape(J_pos, (J_pos.size, 1), order='F'), blastThruster))
+            ocp_solver.set(k, 'p', params)
+            if k + 1 == N:
+                ocp_solver.cost_set(k + 1, 'yref', yref[0:nx])
+            else:
+                ocp_solver.cost_set(k + 1, 'yref', yref)
+        status = ocp_solver.solve()
+        integrator.set('p', params)
+        cost = ocp_solver.get_cost()
+        u = ocp_solver.get(0, "u")
+        integrator.set("x", xcurrent)
+        integrator.set("u", u)
+        assert integrator.solve() == 0
+        uo, Xo, Uo, sto = ctl.solve(xcurrent, yref)
+        assert status == sto == 0
+        assert np.abs(u - uo).max() < TOL
+        assert abs(cost - ctl.cost()) < 1e-6 * max(1.0, abs(cost))
+        xnext = integrator.get("x")
+        assert np.abs(xnext - bo.plant_step(xcurrent, uo, bo.default_params(), P)).max() < 1e-9
+        xcurrent = xnext
+
+
+def test_command_map(cuda_device):
+    B = 16
+    rng = np.random.default_rng(2)
+    x = np.zeros((B, 17))
+    x[:, 3:6] = rng.uniform(-0.3, 0.3, (B, 3))
+    u = rng.uniform(5, 40, (B, 6))
+    mpc = _mpc(5, B)
+    q, t = mpc.command_map(x, u)
+    q, t = q.cpu().numpy(), t.cpu().numpy()
+    for i in range(B):
+        R = bo._rot(*x[i, 3:6])
+        w, a, b, c = q[i]
+        Rq = np.array([[2 * (w * w + a * a) - 1, 2 * (a * b - w * c), 2 * (a * c + w * b)],
+                       [2 * (a * b + w * c), 2 * (w * w + b * b) - 1, 2 * (b * c - w * a)],
+                       [2 * (a * c - w * b), 2 * (b * c + w * a), 2 * (w * w + c * c) - 1]])  # MathUtils.quat2Rot
+        assert np.abs(R - Rq).max() < 1e-14
+        avg = 2.3 * u[i, :4].mean() / 9.81
+        assert abs(t[i] - (0.0014 * avg ** 3 - 0.0263 * avg ** 2 + 0.2464 * avg - 0.0286)) < 1e-14

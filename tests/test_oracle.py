@@ -1,0 +1,212 @@
+"""CPU tests of the oracle: pinned against fixtures generated from the reference's own
+Python (tests/golden/make_golden.py) and cross-checked NumPy <-> C."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from mpc_blaster_b200 import scenarios as sc
+from oracle import blaster_oracle as bo
+from oracle import c_oracle as co
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dyn():
+    return np.load(os.path.join(G, "dynamics_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def ocp():
+    return json.load(open(os.path.join(G, "ocp_golden.json")))
+
+
+def test_dynamics_match_reference_casadi_expression(dyn):
+    """f, df/dx, df/du of the oracle == the reference's f_expl_expr (blastermodel.py:191-201)
+    and its symbolic Jacobians, at 24 seeded points incl. the reference's start point."""
+    P = bo.canonical_problem(20)
+    for i in range(dyn["x"].shape[0]):
+        x, u, p = dyn["x"][i], dyn["u"][i], dyn["p"][i]
+        assert np.abs(bo.f17(x, u, p, P) - dyn["f"][i]).max() < 1e-12
+        fx, fu = bo.jac17(x, u, p, P)
+        assert np.abs(fx - dyn["fx"][i]).max() < 1e-12
+        assert np.abs(fu - dyn["fu"][i]).max() < 1e-12
+        assert np.abs(co.f(P, x, u, p) - dyn["f"][i]).max() < 1e-12
+
+
+def test_jacobian_sparsity_is_the_reference_pattern(dyn):
+    """59 structural nonzeros in df/dx, 32 in df/du."""
+    assert int(dyn["fx_pattern"].sum()) == 59 and int(dyn["fu_pattern"].sum()) == 32
+    P = bo.canonical_problem(20)
+    fx, fu = bo.jac17(dyn["x"][3], dyn["u"][3], dyn["p"][3], P)
+    assert ((fx != 0) <= (dyn["fx_pattern"] != 0)).all()
+    assert ((fu != 0) <= (dyn["fu_pattern"] != 0)).all()
+
+
+def test_problem_data_match_generateController_and_acados_dump(ocp):
+    """Cost matrices, bounds, index sets and options of canonical_problem() equal both what the
+    reference's generateController() sets (blastermodel.py:218-287) and the committed acados
+    dump (src/scripts/acados_ocp_blasterModel.json)."""
+    P = bo.canonical_problem(60)
+    gc, dump = ocp["generateController"], ocp["acados_dump_extract"]
+    W = np.array(gc["W"])
+    assert np.count_nonzero(W - np.diag(np.diag(W))) == 0 and dump["W_offdiag_nnz"] == 0
+    for diag in (np.diag(W), np.array(dump["W_diag"])):
+        assert np.array_equal(diag, np.concatenate([P.Q, P.R]))
+    for diag in (np.diag(np.array(gc["W_e"])), np.array(dump["W_e_diag"])):
+        assert np.array_equal(diag, P.Qt)
+    Vx, Vu = np.array(gc["Vx"]), np.array(gc["Vu"])
+    assert np.array_equal(Vx, np.vstack([np.eye(17), np.zeros((6, 17))]))  # y = [x; u]
+    assert np.array_equal(Vu, np.vstack([np.zeros((17, 6)), np.eye(6)]))
+    assert np.array_equal(np.array(gc["Vx_e"]), np.eye(17))
+    for src in (gc, dump):
+        assert np.array_equal(src["lbx"], P.lbx) and np.array_equal(src["ubx"], P.ubx)
+        assert np.array_equal(src["lbu"], P.lbu) and np.array_equal(src["ubu"], P.ubu)
+        assert list(src["idxbx"]) == list(range(17)) and list(src["idxbu"]) == list(range(6))
+        assert np.allclose(src["parameter_values"], bo.default_params(), rtol=1e-15)
+    assert dump["idxbxe_0"] == list(range(17))  # stage-0 state is an equality
+    d = dump["dims"]
+    assert (d["nx"], d["nu"], d["np"], d["ny"], d["ny_e"], d["nbx"], d["nbu"], d["nbx_e"]) == (17, 6, 25, 23, 17, 17, 6, 0)
+    so = dump["solver_options"]
+    assert so["nlp_solver_type"] == "SQP_RTI" and so["integrator_type"] == "ERK" and so["hessian_approx"] == "GAUSS_NEWTON"
+    assert so["qp_solver"] == "PARTIAL_CONDENSING_HPIPM" and so["qp_solver_cond_N"] == d["N"] == 60
+    assert so["globalization"] == "FIXED_STEP" and so["nlp_solver_step_length"] == 1.0 and so["qp_solver_warm_start"] == 0
+    assert so["levenberg_marquardt"] == 0.0
+    assert len(dump["time_steps_unique"]) == 1 and abs(dump["time_steps_unique"][0] - P.dt) < 1e-15  # uniform dt = 1/30
+    assert gc["solver_options"]["qp_solver_iter_max"] == 500
+
+
+def test_param_packing_is_column_major():
+    """simulation_blaster.py:67 (order='F') == blastermodel.py:203-210 (casadi reshape)."""
+    Jm, Je, Jp = np.arange(6.).reshape(3, 2), 10 + np.arange(9.).reshape(3, 3), 20 + np.arange(9.).reshape(3, 3)
+    p = bo.pack_params(Jm, Je, Jp, 7.0)
+    assert p[1] == Jm[1, 0] and p[3] == Jm[0, 1] and p[6 + 1] == Je[1, 0] and p[15 + 3] == Jp[0, 1] and p[24] == 7.0
+    P = bo.canonical_problem(5)
+    x = np.zeros(17); x[6:9] = [1, 2, 3]
+    u = np.zeros(6); u[4:6] = [0.5, -0.25]
+    f = bo.f17(x, u, p, P)
+    assert np.allclose(f[14:17], Jp @ x[6:9] + Jm @ u[4:6])
+
+
+@pytest.mark.parametrize("variant", [17, 12])
+def test_rk4_sensitivities_are_the_derivative_of_the_discrete_map(variant):
+    P = bo.canonical_problem(10, variant)
+    rng = np.random.default_rng(1)
+    x0, _ = sc.random_setpoints(1, seed=5, nx=P.nx, nu=P.nu)
+    x, u = x0[0], sc.hover_trim(P.nu) + rng.uniform(-1, 1, P.nu) * np.array([1, 1, 1, 1, .02, .02])[:P.nu]
+    p = np.concatenate([0.2 * rng.standard_normal(24), [20.0]])
+    xn, A, B = bo.rk4_sens(x, u, p, P)
+    assert np.abs(xn - bo.plant_step(x, u, p, P)).max() < 1e-15
+    e = 1e-6
+    for j in range(P.nx):
+        d = np.zeros(P.nx); d[j] = e
+        assert np.abs((bo.plant_step(x + d, u, p, P) - bo.plant_step(x - d, u, p, P)) / (2 * e) - A[:, j]).max() < 1e-8
+    for j in range(P.nu):
+        d = np.zeros(P.nu); d[j] = e
+        assert np.abs((bo.plant_step(x, u + d, p, P) - bo.plant_step(x, u - d, p, P)) / (2 * e) - B[:, j]).max() < 1e-8
+    xc, Ac, Bc = co.rk4_sens(P, x, u, p)
+    assert max(np.abs(xc - xn).max(), np.abs(Ac - A).max(), np.abs(Bc - B).max()) < 1e-14
+    assert np.abs(co.plant_step(P, x, u, p)[0] - xn).max() < 1e-15
+
+
+def test_dense_ipm_against_bounded_least_squares():
+    """Box-constrained strictly convex QP without equalities: the IPM optimum equals
+    scipy's BVLS solution of the equivalent least-squares problem."""
+    from scipy.optimize import lsq_linear
+    rng = np.random.default_rng(3)
+    n = 12
+    A = rng.standard_normal((30, n))
+    bvec = rng.standard_normal(30)
+    h = rng.uniform(0.5, 2.0, n)  # diagonal Hessian: scale columns so that A'A is not needed
+    As = np.vstack([np.diag(np.sqrt(h))])
+    t = rng.standard_normal(n) * 2
+    lb, ub = -np.ones(n) * 0.7, np.ones(n) * 0.4
+    # min 1/2 sum h (z - t)^2  ==  1/2 z'Hz + g'z with g = -h t
+    r = bo.ipm_dense(h, -h * t, np.zeros((0, n)), np.zeros(0), lb, ub, tol_comp=1e-12)
+    ref = lsq_linear(As, np.sqrt(h) * t, bounds=(lb, ub), method="bvls", tol=1e-14).x
+    assert r.status == 0 and np.abs(r.z - ref).max() < 1e-9 and np.abs(r.z - np.clip(t, lb, ub)).max() < 1e-9
+
+
+def test_qp_solution_carries_a_kkt_certificate():
+    P = bo.canonical_problem(20)
+    x0, yref = bo.canonical_x0_yref()
+    qp = bo.build_qp(np.zeros((21, 17)), np.zeros((20, 6)), x0, yref, None, P)
+    H, g, C, c, lb, ub = bo.qp_to_dense(qp)
+    r = bo.ipm_dense(H, g, C, c, lb, ub, tol_comp=1e-12)
+    cert = bo.kkt_certificate(H, g, C, c, lb, ub, r.z, r.pi, r.lam_l, r.lam_u)
+    assert r.status == 0
+    assert cert["stat"] < 1e-8 and cert["eq"] < 1e-10 and cert["viol"] < 1e-10 and cert["comp"] < 1e-9 and cert["neg"] == 0
+    # the same primal, certified without the solver's own multipliers
+    pi, ll, lu = bo.multipliers_from_primal(H, g, C, lb, ub, r.z)
+    cert2 = bo.kkt_certificate(H, g, C, c, lb, ub, r.z, pi, ll, lu)
+    assert cert2["stat"] < 1e-6 and cert2["neg"] < 1e-6
+
+
+def test_hover_to_setpoint_behaviour():
+    """Config 1 (simulation_blaster.py:47-48): step 0 saturates all four rotors at 65 N, then
+    the climb rides the vz <= 1 m/s state bound with hover-trim thrust."""
+    P = bo.canonical_problem(20)
+    x0, yref = bo.canonical_x0_yref()
+    simX, simU, iters = bo.closed_loop(P, x0, yref, steps=6)
+    assert np.allclose(simU[0, :4], 65.0, atol=1e-5)
+    assert abs(simU[3, :4].mean() - (9.0 * 9.81 - 2.2 * 9.81) / 4) < 1e-3  # hover trim 16.677 N per rotor
+    assert abs(simX[3, 8] - 1.0) < 1e-6 and simX[:, 8].max() < 1.0 + 1e-7
+    assert max(iters) < 25
+
+
+@pytest.mark.parametrize("variant", [17, 12])
+def test_c_oracle_follows_the_numpy_oracle(variant):
+    """Same Mehrotra iteration, different linear algebra (Riccati-LQ vs dense LU): same
+    iteration counts, same status, primal agreement far below the 1e-6 parity bound."""
+    P = bo.canonical_problem(20, variant)
+    B = 6
+    x0, yref = sc.random_setpoints(B, seed=77, nx=P.nx, nu=P.nu)
+    c = co.BatchRTI(P, B, nthreads=2)
+    ctls = [bo.RTIOracle(P) for _ in range(B)]
+    x = x0.copy()
+    for step in range(3):
+        u0, X, U, st = c.solve(x, yref)
+        for i in range(B):
+            ui, Xi, Ui, sti = ctls[i].solve(x[i], yref[i])
+            assert sti == st[i] == 0 and ctls[i].last[1].iters == c.iters[i]
+            assert np.abs(Ui - U[i]).max() < 1e-7 and np.abs(Xi - X[i]).max() < 1e-8
+        x = co.plant_step(P, x, u0)
+
+
+def test_tight_tolerance_converges_to_the_unique_optimum():
+    """Driving the complementarity tolerance from HPIPM's 1e-8 to 1e-12 moves the well-determined
+    part of the solution (states, thrusts of the first stage) by < 1e-4: u0 is insensitive."""
+    P = bo.canonical_problem(20)
+    x0, yref = sc.random_setpoints(4, seed=5)
+    a = co.BatchRTI(P, 4, tol_comp=1e-8)
+    b = co.BatchRTI(P, 4, tol_comp=1e-12)
+    for o in (a, b):
+        o.reset(x0, sc.hover_trim())
+    ua, Xa, _, sa = a.solve(x0, yref)
+    ub, Xb, _, sb = b.solve(x0, yref)
+    assert (sa == 0).all() and (sb == 0).all() and (b.iters >= a.iters).all()
+    assert np.abs(ua[:, :4] - ub[:, :4]).max() < 1e-4 and np.abs(Xa - Xb).max() < 1e-4
+
+
+def test_infeasible_qp_is_reported_not_hidden():
+    P = bo.canonical_problem(20)
+    x0, yref = sc.random_setpoints(2, seed=15)
+    x0[1, 6] = 3.0  # vx = 3 m/s against a +-1 m/s bound on stage 1
+    c = co.BatchRTI(P, 2)
+    c.reset(x0, sc.hover_trim())
+    _, _, _, st = c.solve(x0, yref)
+    assert st[0] == 0 and st[1] in (2, 3, 4)
+    ctl = bo.RTIOracle(P)
+    ctl.reset(x0[1], sc.hover_trim())
+    assert ctl.solve(x0[1], yref[1])[3] == st[1]
+
+
+def test_cost_matches_definition():
+    P = bo.canonical_problem(5)
+    rng = np.random.default_rng(0)
+    X, U, yref = rng.standard_normal((6, 17)), rng.standard_normal((5, 6)), rng.standard_normal(23)
+    ref = sum(0.5 * P.dt * (P.Q @ (X[k] - yref[:17]) ** 2 + P.R @ (U[k] - yref[17:]) ** 2) for k in range(5))
+    ref += 0.5 * P.Qt @ (X[5] - yref[:17]) ** 2
+    assert abs(bo.stage_cost(X, U, yref, P) - ref) < 1e-9 * abs(ref)
