@@ -462,10 +462,16 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
                 const sptr vr = sptr_add(vr0, (j & 1) * L::NXP);
                 const T hdj = warp_shfl(Hd, j), dsj = warp_shfl(dsq, j);
                 const bool piv = (lane == j);
+                T v[NX];
+#ifndef MPCB_PIVOT_VIA_SHFL  // shared-memory broadcast (default): same latency as 34 shuffles, less MIO pressure at high occupancy
                 sp_row_store<0, NX>(vr, w, piv);
                 warp_sync();
-                T v[NX];
                 sp_row_load<0, NX>(vr, v);
+#else
+                (void)vr;
+                MPCB_UNROLL
+                for (int c = 0; c < NX; c++) v[c] = warp_shfl(w[c], j);
+#endif
                 T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
                 MPCB_UNROLL
                 for (int c = 0; c + 3 < NX; c += 4) {
