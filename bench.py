@@ -117,7 +117,8 @@ def cpu_steps(steps: int, warmup: int, batch: int, horizon: int, variant: int):
     from oracle import c_oracle as co
     P = bo.canonical_problem(horizon, variant)
     x0, yref, trim = workload(0, batch, variant)
-    orc = co.BatchRTI(P, batch)
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+    orc = co.BatchRTI(P, batch, nthreads=len(os.sched_getaffinity(0)))
     times = []
     for i in range(warmup + steps):
         orc.reset(x0, trim)
