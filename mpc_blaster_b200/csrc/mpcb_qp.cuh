@@ -682,10 +682,12 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         }
     }
 
-    // ---------------- RTI update: X += dx, U += du (full step)
+    // ---------------- RTI update: X += dx, U += du (full step).  A failed QP (status != 0: NaN,
+    // max-iter, min-step = infeasible, breakdown) leaves the iterate untouched, so one bad solve
+    // cannot poison the warm start of the following control steps.
     warp_sync();
     MPCB_UNROLL4
-    for (int k = 0; k <= N; k++) {
+    for (int k = 0; k <= (status == ST_OK ? N : -1); k++) {
         const T *wk = ws + (size_t)k * L::STAGE;
         if (lane < NU) {
             if (k < N) Ui[(size_t)k * NU + lane] += wk[L::O_Z + lane];

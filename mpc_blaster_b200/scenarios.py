@@ -27,8 +27,11 @@ def hover_to_setpoint():
     return x0, yref
 
 
-def random_setpoints(B: int, seed: int = 1234, nx: int = 17, nu: int = 6):
-    """Configs 2/4/5: randomised x0 inside the bounds and a random position set-point."""
+def random_setpoints(B: int, seed: int = 1234, nx: int = 17, nu: int = 6, alpha_max: float = 0.5):
+    """Configs 2/4/5: randomised x0 inside the bounds and a random position set-point.
+    ``alpha_max`` bounds the initial gimbal deflection; large deflections (0.5 rad) are fine for
+    single solves but, with the +-5 deg/s swivel-rate and body-rate bounds, make the hard vx/vy <= 1 m/s
+    state bounds unreachable a few control steps into a closed loop, so config 4 uses 0.05."""
     rng = np.random.default_rng(seed)
     x0 = np.zeros((B, NX_FULL))
     x0[:, 0:2] = rng.uniform(-1.0, 1.0, (B, 2))
@@ -37,8 +40,8 @@ def random_setpoints(B: int, seed: int = 1234, nx: int = 17, nu: int = 6):
     x0[:, 5] = rng.uniform(-0.30, 0.30, B)
     x0[:, 6:9] = rng.uniform(-0.3, 0.3, (B, 3))
     x0[:, 9:12] = rng.uniform(-0.03, 0.03, (B, 3))
-    x0[:, 12] = rng.uniform(0.0, 0.5, B)
-    x0[:, 13] = rng.uniform(-0.3, 0.3, B)
+    x0[:, 12] = rng.uniform(0.0, alpha_max, B)
+    x0[:, 13] = rng.uniform(-0.6 * alpha_max, 0.6 * alpha_max, B)
     yref = np.zeros((B, NX_FULL + NU_FULL))
     yref[:, 0:2] = rng.uniform(-1.2, 1.2, (B, 2))
     yref[:, 2] = rng.uniform(0.5, 4.5, B)
@@ -73,3 +76,29 @@ def hover_trim(nu: int = 6, mass: float = 9.0, T_blast: float = 2.2 * 9.81) -> n
     u = np.zeros(nu)
     u[:4] = (mass * 9.81 - T_blast) / 4.0
     return u
+
+
+def closed_loop_setpoints(B: int, seed: int = 3456, nx: int = 17, nu: int = 6):
+    """Config 4 (closed-loop Monte-Carlo): the reference's hover-to-set-point manoeuvre
+    (simulation_blaster.py:47-48) randomised -- mostly vertical moves (|dz| <= 1.5 m) with small
+    lateral offsets (<= 0.3 m) and small initial velocities.  With the reference's tight hard
+    state bounds (|v| <= 1 m/s, body rates and swivel rates <= 5 deg/s) and a 0.67 s horizon,
+    larger lateral moves become recursively infeasible a few dozen steps in."""
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((B, NX_FULL))
+    x0[:, 0:2] = rng.uniform(-1.0, 1.0, (B, 2))
+    x0[:, 2] = rng.uniform(1.0, 3.5, B)
+    x0[:, 3:5] = rng.uniform(-0.02, 0.02, (B, 2))
+    x0[:, 5] = rng.uniform(-0.30, 0.30, B)
+    x0[:, 6:9] = rng.uniform(-0.1, 0.1, (B, 3))
+    x0[:, 9:12] = rng.uniform(-0.02, 0.02, (B, 3))
+    x0[:, 12] = rng.uniform(0.0, 0.05, B)
+    x0[:, 13] = rng.uniform(-0.03, 0.03, B)
+    yref = np.zeros((B, NX_FULL + NU_FULL))
+    yref[:, 0:2] = x0[:, 0:2] + rng.uniform(-0.3, 0.3, (B, 2))
+    yref[:, 2] = np.clip(x0[:, 2] + rng.uniform(-1.5, 1.5, B), 0.5, 4.5)
+    if nx == NX_FULL:
+        return x0, yref
+    y = np.zeros((B, nx + nu))
+    y[:, :nx] = yref[:, :nx]
+    return np.ascontiguousarray(x0[:, :nx]), y

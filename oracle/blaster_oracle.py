@@ -612,8 +612,9 @@ class RTIOracle:
         du, dx, r = solve_qp(qp, **self.ipm_opts)
         # FIXED_STEP, step length 1.0 (JSON globalization / nlp_solver_step_length):
         # full step, no SQP-level line search; [upstream D5] iterate kept, not shifted
-        self.X = self.X + dx
-        self.U = self.U + du
+        if r.status == 0:  # a failed QP leaves the iterate untouched (same rule as the product)
+            self.X = self.X + dx
+            self.U = self.U + du
         self.last = (qp, r)
         self._yref = yref
         return self.U[0].copy(), self.X.copy(), self.U.copy(), r.status

@@ -473,7 +473,8 @@ static int SFX(rti_solve)(const orc_problem *P, double *X, double *U, const doub
     /* [upstream D3] x0 pinned: dx_0 = x0 - X_0 */
     for (int i = 0; i < NX; i++) w.z[NU + i] = x0[i] - X[i];
     int status = SFX(ipm)(P, &w, N, iters);
-    for (int k = 0; k <= N; k++) {
+    /* a failed QP leaves the iterate untouched (same rule as the product) */
+    for (int k = 0; k <= (status == 0 ? N : -1); k++) {
         if (k < N) for (int j = 0; j < NU; j++) U[(size_t)k * NU + j] += w.z[(size_t)k * NZ + j];
         for (int i = 0; i < NX; i++) X[(size_t)k * NX + i] += w.z[(size_t)k * NZ + NU + i];
     }
