@@ -91,6 +91,18 @@ int mpcb_solve(mpcb_handle *h, const double *x0, const double *yref, int yref_mo
 int mpcb_solve_host(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
                     double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B);
 
+/* `sqp_iters` SQP iterations on the same (x0, yref, p) -- each one re-linearises about the iterate
+ * the previous one produced (SQP instead of SQP_RTI; the reference's options carry
+ * nlp_solver_max_iter = 100 but select SQP_RTI, blastermodel.py:278).  status/iters are those of
+ * the last iteration. */
+int mpcb_solve_sqp(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+                   int sqp_iters, double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B, void *stream);
+
+/* Shift the stored iterate one stage forward (X_k <- X_{k+1}, U_k <- U_{k+1}, last stage repeated):
+ * the standard warm start between control steps.  The reference's scripts never shift
+ * (simulation_blaster.py:56-105), so this is opt-in. */
+int mpcb_shift(mpcb_handle *h, int B, void *stream);
+
 /* Plant step x+ = RK4(x,u,p) over dt for B instances (AcadosSimSolver of blastermodel.py:290).
  * p_mode: MPCB_SHARED or MPCB_PER_INSTANCE. */
 int mpcb_plant_step(mpcb_handle *h, const double *x, const double *u, const double *p, int p_mode, double *xnext,

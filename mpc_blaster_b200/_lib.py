@@ -28,7 +28,7 @@ class MpcbConfig(C.Structure):
 EXPORTS = ["mpcb_config_default", "mpcb_create", "mpcb_destroy", "mpcb_last_error", "mpcb_nx", "mpcb_nu", "mpcb_horizon",
            "mpcb_reset", "mpcb_solve", "mpcb_solve_host", "mpcb_plant_step", "mpcb_closed_loop", "mpcb_cost",
            "mpcb_get_iterate", "mpcb_set_iterate", "mpcb_debug_linearize", "mpcb_kernel_launches", "mpcb_command_map",
-           "mpcb_profile", "mpcb_last_kernel_ms", "mpcb_fp64_peak"]
+           "mpcb_profile", "mpcb_last_kernel_ms", "mpcb_fp64_peak", "mpcb_solve_sqp", "mpcb_shift"]
 
 _lib = None
 
@@ -61,6 +61,8 @@ def load() -> C.CDLL:
         getattr(lib, f).argtypes = [vp]
     lib.mpcb_reset.argtypes = [vp, dp, dp, C.c_int, C.c_int, vp]
     lib.mpcb_solve.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip, C.c_int, vp]
+    lib.mpcb_solve_sqp.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, C.c_int, dp, dp, dp, ip, ip, C.c_int, vp]
+    lib.mpcb_shift.argtypes = [vp, C.c_int, vp]
     lib.mpcb_solve_host.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip, C.c_int]
     lib.mpcb_plant_step.argtypes = [vp, dp, dp, dp, C.c_int, dp, C.c_int, vp]
     lib.mpcb_closed_loop.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, C.c_int, dp, ip, ip, C.c_int, vp]

@@ -157,6 +157,21 @@ __global__ void debug_copy_kernel(const __grid_constant__ Params P, const double
     else b[(inst * N + k) * NX + (e - L::NZ * NX)] = wk[L::O_B + e - L::NZ * NX];
 }
 
+// Horizon shift of the stored iterate (the usual RTI companion; the reference's
+// scripts never shift): X_k <- X_{k+1}, U_k <- U_{k+1}, the last stage is repeated.
+template <int NX, int NU>
+__global__ void shift_kernel(const __grid_constant__ Params P, double *__restrict__ X, double *__restrict__ U, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int N = P.N;
+    double *Xi = X + (size_t)i * (N + 1) * NX, *Ui = U + (size_t)i * N * NU;
+    for (int k = 0; k < N; k++)
+        for (int j = 0; j < NX; j++) Xi[(size_t)k * NX + j] = Xi[(size_t)(k + 1) * NX + j];
+    for (int k = 0; k + 1 < N; k++)
+        for (int j = 0; j < NU; j++) Ui[(size_t)k * NU + j] = Ui[(size_t)(k + 1) * NU + j];
+}
+
 // closed-loop bookkeeping: x <- xnext, count failures / iterations
 template <int NX>
 __global__ void loop_book_kernel(double *__restrict__ x, const double *__restrict__ xn, const int32_t *__restrict__ status,
@@ -595,6 +610,30 @@ int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BA
         g_launches += 2;
     }
     CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_shift(mpcb_handle *h, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (B == 0) return 0;
+    const unsigned grid = (B + 127) / 128;
+    if (h->nx == 17) shift_kernel<17, 6><<<grid, 128, 0, (cudaStream_t)stream>>>(h->P, h->X, h->U, B);
+    else shift_kernel<12, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(h->P, h->X, h->U, B);
+    g_launches += 1;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_solve_sqp(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+                   int sqp_iters, double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B, void *stream)
+{
+    if (sqp_iters < 1) return fail(h, "sqp_iters must be >= 1");
+    for (int it = 0; it < sqp_iters; it++) {
+        const bool last = it + 1 == sqp_iters;
+        if (mpcb_solve(h, x0, yref, yref_mode, p, p_mode, u0, last ? X : nullptr, last ? U : nullptr, status, iters, B, stream))
+            return -1;
+    }
     return 0;
 }
 

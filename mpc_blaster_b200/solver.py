@@ -35,6 +35,32 @@ class MpcbError(RuntimeError):
     pass
 
 
+def acados_json_args(path, N=None) -> dict:
+    """Read the OCP data of an acados dump (the on-disk format the reference writes,
+    blastermodel.py:289) into ``BlasterMPC`` constructor arguments.  dt = tf / dims.N is kept
+    when the horizon is overridden."""
+    import json
+    d = json.load(open(path))
+    nx, nu = int(d["dims"]["nx"]), int(d["dims"]["nu"])
+    if (nx, nu) != (17, 6):
+        raise ValueError("the dump is not the BLASTER OCP (nx, nu) = (17, 6)")
+    so = d["solver_options"]
+    if so["nlp_solver_type"] != "SQP_RTI" or so["integrator_type"] != "ERK" or so["hessian_approx"] != "GAUSS_NEWTON":
+        raise ValueError("only the reference's SQP_RTI + ERK + GAUSS_NEWTON configuration is supported")
+    if d["cost"]["cost_type"] != "LINEAR_LS" or d["cost"]["cost_type_e"] != "LINEAR_LS":
+        raise ValueError("only LINEAR_LS costs are supported")
+    W, We = np.array(d["cost"]["W"], dtype=np.float64), np.array(d["cost"]["W_e"], dtype=np.float64)
+    cons = d["constraints"]
+    if list(cons["idxbx"]) != list(range(nx)) or list(cons["idxbu"]) != list(range(nu)):
+        raise ValueError("expected box bounds on every state and input")
+    Nf = int(d["dims"]["N"])
+    dt = float(so["tf"]) / Nf
+    N = Nf if N is None else int(N)
+    return dict(N=N, Tf=dt * N, Q=W[:nx, :nx], R=W[nx:, nx:], Q_t=We, blastThruster=float(d["parameter_values"][-1]),
+                statesBound=np.array([cons["lbx"], cons["ubx"]]), controlBound=np.array([cons["lbu"], cons["ubu"]]),
+                ipm_max_iter=int(so["qp_solver_iter_max"]))
+
+
 class BlasterMPC:
     """B independent BLASTER controllers solved together on one GPU.
 
@@ -135,7 +161,13 @@ class BlasterMPC:
             per = int(ui is not None and ui.dim() == 2)
             self._check(self.lib.mpcb_reset(self._h, self._p(xi), self._p(ui), per, B, self._stream()), "mpcb_reset")
 
-    def solve(self, x0, yref, p=None, want_traj: bool = True):
+    def shift(self, B: int | None = None):
+        """Shift the stored iterate one stage forward (opt-in; the reference never shifts)."""
+        B = self.batch if B is None else B
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mpcb_shift(self._h, B, self._stream()), "mpcb_shift")
+
+    def solve(self, x0, yref, p=None, want_traj: bool = True, sqp_iters: int = 1):
         """One SQP-RTI iteration for every instance: returns (u0[B,nu], X[B,N+1,nx],
         U[B,N,nu], status[B] int32).  yref: [ny] | [B,ny] | [B,N+1,ny]; p: None | [25] |
         [B,25] | [B,N,25].  The iterate is kept in the handle for the next call (un-shifted
@@ -155,11 +187,28 @@ class BlasterMPC:
             U = torch.empty((B, self.N, self.nu), dtype=torch.float64, device=self.device) if want_traj else None
             status = torch.empty((B,), dtype=torch.int32, device=self.device)
             self.iters = torch.empty((B,), dtype=torch.int32, device=self.device)
-            self._check(self.lib.mpcb_solve(self._h, self._p(x0), self._p(yref), ymode, self._p(pt), pmode, self._p(u0),
-                                            self._p(X), self._p(U), self._p(status), self._p(self.iters), B, self._stream()),
-                        "mpcb_solve")
+            if sqp_iters == 1:
+                rc = self.lib.mpcb_solve(self._h, self._p(x0), self._p(yref), ymode, self._p(pt), pmode, self._p(u0),
+                                         self._p(X), self._p(U), self._p(status), self._p(self.iters), B, self._stream())
+            else:  # full SQP: re-linearise sqp_iters times on the same data
+                rc = self.lib.mpcb_solve_sqp(self._h, self._p(x0), self._p(yref), ymode, self._p(pt), pmode, int(sqp_iters),
+                                             self._p(u0), self._p(X), self._p(U), self._p(status), self._p(self.iters), B,
+                                             self._stream())
+            self._check(rc, "mpcb_solve")
             self._yref = yref
         return u0, X, U, status
+
+    @classmethod
+    def from_acados_json(cls, path, *, N=None, batch=1, variant=17, mass=9.0, J=None, l_x=0.3434, l_y=0.3475, c=0.03, **kw):
+        """Build a solver from an acados OCP dump such as the reference's
+        src/scripts/acados_ocp_blasterModel.json (written at blastermodel.py:289): weights,
+        bounds, horizon and tf are read from the file; the physical constants, which the dump does
+        not contain (they are baked into the generated model code), come from the arguments
+        (defaults = simulation_blaster.py:12-21)."""
+        a = acados_json_args(path, N=N)
+        J = np.diag([0.50781, 0.47314, 0.72975]) if J is None else J
+        return cls(mass, J, l_x, l_y, a["N"], a["Tf"], c, a["Q"], a["R"], a["Q_t"], a["blastThruster"], a["statesBound"],
+                   a["controlBound"], batch=batch, variant=variant, **kw)
 
     def solve_host(self, x0, yref, p=None, want_traj: bool = False):
         """Same through ``mpcb_solve_host``: NumPy in, NumPy out, copies inside the call."""

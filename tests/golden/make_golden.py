@@ -281,6 +281,15 @@ def main():
                time_steps_unique=sorted(set(np.round(dump["solver_options"]["time_steps"], 15).tolist())),
                solver_options={k: dump["solver_options"].get(k) for k in keep_opts})
     json.dump(dict(generateController=got, acados_dump_extract=ext), open(os.path.join(HERE, "ocp_golden.json"), "w"), indent=1)
+    # a subset of the dump in its own (acados) format, for the JSON-loader tests
+    sub = dict(dims={k: dump["dims"][k] for k in ("N", "nx", "nu", "np", "ny", "ny_e", "nbx", "nbu")},
+               cost={k: dump["cost"][k] for k in ("W", "W_e", "cost_type", "cost_type_e")},
+               constraints={k: dump["constraints"][k] for k in ("lbx", "ubx", "lbu", "ubu", "idxbx", "idxbu")},
+               parameter_values=dump["parameter_values"],
+               solver_options={k: dump["solver_options"][k] for k in ("tf", "nlp_solver_type", "integrator_type", "hessian_approx",
+                                                                      "qp_solver", "qp_solver_cond_N", "qp_solver_iter_max",
+                                                                      "globalization", "nlp_solver_step_length", "qp_solver_warm_start")})
+    json.dump(sub, open(os.path.join(HERE, "acados_ocp_subset.json"), "w"))
     print("wrote", os.listdir(HERE))
 
 

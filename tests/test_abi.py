@@ -60,3 +60,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_acados_json_loader_reads_the_reference_dump_format():
+    """the on-disk format.  tests/golden/acados_ocp_subset.json is a subset, in
+    acados' own layout, of the dump the reference commits (src/scripts/acados_ocp_blasterModel.json)."""
+    import numpy as np
+    from mpc_blaster_b200.solver import acados_json_args
+    from oracle import blaster_oracle as bo
+    a = acados_json_args(os.path.join(ROOT, "tests", "golden", "acados_ocp_subset.json"))
+    P = bo.canonical_problem(60)
+    assert a["N"] == 60 and abs(a["Tf"] - 2.0) < 1e-15 and a["ipm_max_iter"] == 500
+    assert np.array_equal(np.diag(a["Q"]), P.Q) and np.array_equal(np.diag(a["R"]), P.R) and np.array_equal(np.diag(a["Q_t"]), P.Qt)
+    assert np.array_equal(a["statesBound"], np.array([P.lbx, P.ubx])) and np.array_equal(a["controlBound"], np.array([P.lbu, P.ubu]))
+    assert abs(a["blastThruster"] - 2.2 * 9.81) < 1e-12
+    b = acados_json_args(os.path.join(ROOT, "tests", "golden", "acados_ocp_subset.json"), N=20)
+    assert b["N"] == 20 and abs(b["Tf"] - 20 / 30) < 1e-15  # dt = 1/30 kept

@@ -285,3 +285,41 @@ def test_command_map(cuda_device):
         assert np.abs(R - Rq).max() < 1e-14
         avg = 2.3 * u[i, :4].mean() / 9.81
         assert abs(t[i] - (0.0014 * avg ** 3 - 0.0263 * avg ** 2 + 0.2464 * avg - 0.0286)) < 1e-14
+
+
+def test_sqp_iterations_and_shift(cuda_device):
+    """several SQP iterations on the same data (each re-linearises about the last
+    iterate) equal the oracle doing the same, and converge (the last step is tiny); the horizon
+    shift moves every stage forward and repeats the last one."""
+    B, N = 32, 20
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(B, seed=77)
+    mpc = _mpc(N, B)
+    orc = co.BatchRTI(P, B)
+    trim = sc.hover_trim()
+    mpc.reset(x0, trim)
+    orc.reset(x0, trim)
+    u0, X, U, st = mpc.solve(x0, yref, sqp_iters=4)
+    for _ in range(4):
+        Xprev = orc.X.copy()
+        uo, Xo, Uo, sto = orc.solve(x0, yref)
+    ok = sto == 0
+    assert (st.cpu().numpy() == sto).all() and ok.mean() > 0.9
+    assert np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < 1e-5 and np.abs(u0.cpu().numpy()[ok, :4] - uo[ok, :4]).max() < 1e-5
+    assert np.abs(Xo[ok] - Xprev[ok]).max() < 1e-3  # 4th SQP step is small: converging
+    mpc.shift()
+    Xs, Us = mpc.iterate()
+    assert torch.equal(Xs[:, :-1], X[:, 1:]) and torch.equal(Xs[:, -1], X[:, -1])
+    assert torch.equal(Us[:, :-1], U[:, 1:]) and torch.equal(Us[:, -1], U[:, -1])
+
+
+def test_from_acados_json_equals_canonical(cuda_device):
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "acados_ocp_subset.json")
+    from mpc_blaster_b200 import BlasterMPC
+    B = 16
+    x0, yref = sc.random_setpoints(B, seed=5)
+    a = BlasterMPC.from_acados_json(path, N=20, batch=B, ipm_max_iter=60)
+    b = _mpc(20, B)
+    for s, t in zip(a.solve(x0, yref), b.solve(x0, yref)):
+        assert torch.equal(s, t)
