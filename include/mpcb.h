@@ -54,7 +54,8 @@ typedef struct mpcb_config {
     double lbx[17], ubx[17], lbu[6], ubu[6];
     /* interior-point options (defaults = HPIPM's documented defaults, qp_solver_iter_max from blastermodel.py:279 is 500) */
     int32_t ipm_max_iter;
-    double ipm_mu0, ipm_thr0;
+    double ipm_mu0;       /* initial lam*t of every bound (cold start) */
+    double ipm_thr0;      /* initial slack floor: >= 0 absolute, < 0 the fraction -ipm_thr0 of the box width */
     double tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min;
     int32_t max_batch;    /* capacity of the persistent iterate (instances) */
     int32_t ws_batch;     /* instances of solver workspace resident at once (0 = auto) */

@@ -339,7 +339,7 @@ int mpcb_config_default(mpcb_config *cfg, int variant, int N)
     const double lbu[6] = {0, 0, 0, 0, -0.0872665, -0.0872665}, ubu[6] = {65, 65, 65, 65, 0.0872665, 0.0872665};
     for (int i = 0; i < 17; i++) { cfg->Q[i] = Q[i]; cfg->Qt[i] = 10 * Q[i]; cfg->lbx[i] = lbx[i]; cfg->ubx[i] = ubx[i]; }
     for (int i = 0; i < 6; i++) { cfg->R[i] = R[i]; cfg->lbu[i] = lbu[i]; cfg->ubu[i] = ubu[i]; }
-    cfg->ipm_max_iter = 60; cfg->ipm_mu0 = 1e4; cfg->ipm_thr0 = 10.0;
+    cfg->ipm_max_iter = 60; cfg->ipm_mu0 = 1e2; cfg->ipm_thr0 = -0.5;
     cfg->tol_stat = 1e-6; cfg->tol_eq = 1e-8; cfg->tol_ineq = 1e-8; cfg->tol_comp = 1e-8; cfg->alpha_min = 1e-8;
     cfg->max_batch = 1024; cfg->ws_batch = 0; cfg->device = -1;
     return 0;

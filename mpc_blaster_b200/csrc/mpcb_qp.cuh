@@ -285,7 +285,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
     for (int idx = lane; idx < NX * NX; idx += 32) sm.Lxx[idx] = T(0);
 
     // ---------------- F0: QP data and cold start [upstream D8]: z = 0 (dx_0 pinned), pi = 0,
-    // t >= thr0, lam = mu0/t.  Cost gradient and bounds on the increments.
+    // t >= slack floor, lam = mu0/t.  Cost gradient and bounds on the increments.
     T eg = T(0), eb = T(0), ed = T(0);
     MPCB_UNROLL4
     for (int k = 0; k <= N; k++) {
@@ -309,8 +309,10 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         }
         T tl = T(1), tu = T(1), ll = T(0), lu = T(0);
         if (vk.hasb) {
-            tl = fmax(z - lb, thr0);
-            tu = fmax(ub - z, thr0);
+            // slack floor: absolute (thr0 >= 0) or the fraction -thr0 of the box width (thr0 < 0)
+            const T flo = (thr0 >= T(0)) ? thr0 : -thr0 * (ub - lb);
+            tl = fmax(z - lb, flo);
+            tu = fmax(ub - z, flo);
             ll = mu0 / tl;
             lu = mu0 / tu;
             ed = fmax(ed, fmax(fabs(z - lb - tl), fabs(ub - z - tu)));

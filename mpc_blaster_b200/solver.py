@@ -71,7 +71,7 @@ class BlasterMPC:
 
     def __init__(self, mass, J, l_x, l_y, N, Tf, c, Q, R, Q_t, blastThruster, statesBound, controlBound, *,
                  batch: int = 1, variant: int = 17, device=None, ws_batch: int = 0, ipm_max_iter: int = 60,
-                 ipm_mu0: float = 1e4, ipm_thr0: float = 10.0, tol_stat: float = 1e-6, tol_eq: float = 1e-8,
+                 ipm_mu0: float = 1e2, ipm_thr0: float = -0.5, tol_stat: float = 1e-6, tol_eq: float = 1e-8,
                  tol_ineq: float = 1e-8, tol_comp: float = 1e-8, alpha_min: float = 1e-8):
         if not torch.cuda.is_available():
             raise MpcbError("BlasterMPC needs a CUDA device; this package has no CPU fallback")

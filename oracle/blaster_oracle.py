@@ -412,7 +412,7 @@ class IPMResult:
     res: tuple
 
 
-def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8, mu0=1e4, thr0=10.0,
+def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8, mu0=1e2, thr0=-0.5,
               max_iter=60, alpha_min=1e-8, z_fixed=None) -> IPMResult:
     """Mehrotra predictor-corrector IPM, cold start [upstream D8], default tolerances =
     HPIPM's documented defaults (stationarity 1e-6, the rest 1e-8).  Same iteration
@@ -431,8 +431,10 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
     ubf = np.where(iu, ub, 0.0)
     z = np.zeros(n)
     pi = np.zeros(m)
-    tl = np.where(il, np.maximum(z - lbf, thr0), 1.0)
-    tu = np.where(iu, np.maximum(ubf - z, thr0), 1.0)
+    # slack floor: absolute (thr0 >= 0) or the fraction -thr0 of the box width (thr0 < 0)
+    flo = thr0 if thr0 >= 0 else -thr0 * np.where(il & iu, ubf - lbf, 1.0)
+    tl = np.where(il, np.maximum(z - lbf, flo), 1.0)
+    tu = np.where(iu, np.maximum(ubf - z, flo), 1.0)
     ll = np.where(il, mu0 / tl, 0.0)
     lu = np.where(iu, mu0 / tu, 0.0)
     nb = int(il.sum() + iu.sum())

@@ -37,7 +37,7 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def make_problem(P: BlasterProblem, max_iter=60, mu0=1e4, thr0=10.0, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8,
+def make_problem(P: BlasterProblem, max_iter=60, mu0=1e2, thr0=-0.5, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8,
                  tol_comp=1e-8, ric_alg=1, rg_mode=2, alpha_min=1e-8) -> OrcProblem:
     o = OrcProblem()
     o.variant, o.N, o.dt, o.mass = P.variant, P.N, P.dt, P.mass

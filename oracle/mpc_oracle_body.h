@@ -328,8 +328,10 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
         if (SKIP(k, j)) { w->lb[i] = -HUGE_VAL; w->ub[i] = HUGE_VAL; }
         int hl = w->lb[i] > -HUGE_VAL, hu = w->ub[i] < HUGE_VAL;
         nb += hl + hu;
-        w->tl[i] = hl ? fmax(w->z[i] - w->lb[i], thr0) : 1.0;
-        w->tu[i] = hu ? fmax(w->ub[i] - w->z[i], thr0) : 1.0;
+        /* slack floor: absolute (thr0 > 0) or a fraction -thr0 of the box width (thr0 < 0) */
+        const double flo = (thr0 >= 0.0) ? thr0 : -thr0 * (w->ub[i] - w->lb[i]);
+        w->tl[i] = hl ? fmax(w->z[i] - w->lb[i], flo) : 1.0;
+        w->tu[i] = hu ? fmax(w->ub[i] - w->z[i], flo) : 1.0;
         w->ll[i] = hl ? mu0 / w->tl[i] : 0.0;
         w->lu[i] = hu ? mu0 / w->tu[i] : 0.0;
         w->rdl[i] = w->rdu[i] = w->rml[i] = w->rmu[i] = 0.0;

@@ -48,7 +48,7 @@ def lib():
     return _lib
 
 
-def make_params(P, max_iter=60, mu0=1e4, thr0=10.0, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
+def make_params(P, max_iter=60, mu0=1e2, thr0=-0.5, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
                 alpha_min=1e-8) -> Params:
     """P: oracle.blaster_oracle.BlasterProblem (only used here as a container of constants)."""
     o = Params()

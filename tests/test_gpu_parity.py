@@ -289,8 +289,9 @@ def test_command_map(cuda_device):
 
 def test_sqp_iterations_and_shift(cuda_device):
     """several SQP iterations on the same data (each re-linearises about the last
-    iterate) equal the oracle doing the same, and converge (the last step is tiny); the horizon
-    shift moves every stage forward and repeats the last one."""
+    iterate) equal the oracle doing the same (full steps without globalisation, as the reference's
+    FIXED_STEP option prescribes -- which is not guaranteed to converge); the horizon shift moves every
+    stage forward and repeats the last one."""
     B, N = 32, 20
     P = bo.canonical_problem(N)
     x0, yref = sc.random_setpoints(B, seed=77)
@@ -301,12 +302,10 @@ def test_sqp_iterations_and_shift(cuda_device):
     orc.reset(x0, trim)
     u0, X, U, st = mpc.solve(x0, yref, sqp_iters=4)
     for _ in range(4):
-        Xprev = orc.X.copy()
         uo, Xo, Uo, sto = orc.solve(x0, yref)
     ok = sto == 0
     assert (st.cpu().numpy() == sto).all() and ok.mean() > 0.9
     assert np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < 1e-5 and np.abs(u0.cpu().numpy()[ok, :4] - uo[ok, :4]).max() < 1e-5
-    assert np.abs(Xo[ok] - Xprev[ok]).max() < 1e-3  # 4th SQP step is small: converging
     mpc.shift()
     Xs, Us = mpc.iterate()
     assert torch.equal(Xs[:, :-1], X[:, 1:]) and torch.equal(Xs[:, -1], X[:, -1])
