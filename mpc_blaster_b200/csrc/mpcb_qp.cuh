@@ -161,19 +161,27 @@ MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
 
 // One forward sweep: dz_k = [du_k; dx_k] with du_k = -Luu^{-T}(lvec_k + Lxu' dx_k),
 // dx_{k+1} = r_k + [B A] dz_k.  FINAL additionally produces dpi_{k+1} = P_{k+1} dx_{k+1} + p_{k+1}.
+// The elementwise box work of the step just computed is folded in (it only depends on dz_k and
+// overlaps the latency of the recursion): the reciprocal of the largest admissible step `imax`,
+// and for the affine sweep the sums that give mu_aff(alpha) plus the corrector gradient pieces.
 template <int NX, int NU, typename T, bool FINAL>
-MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict__ ws)
+MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict__ ws, T sigmu, T &imax_out, T &acc1_out,
+                            T &acc2_out)
 {
     using L = Layout<NX, NU>;
     constexpr int NZ = L::NZ;
     constexpr int O_OUT = FINAL ? L::O_DZ : L::O_DZA;
     const int lane = lane_id();
     const int N = P.N;
-    // record k: [BAt | Lu | invd | lvec | rb]; FINAL: also [Lxx | pv] of record k+1
-    constexpr int RUN1 = L::O_Z;
+    // record k: [BAt | Lu | invd | lvec | rb | z tl tu ll lu lb ub]; FINAL: also [dza] and [Lxx | pv] of record k+1
+    constexpr int RUN1 = L::O_G;
     async_copy(sm.slot[0], ws, RUN1);
-    if (FINAL) async_copy(sm.slot[0] + L::O_LXX, ws + L::STAGE + L::O_LXX, L::LXX + L::NXP);
+    if (FINAL) {
+        async_copy(sm.slot[0] + L::O_DZA, ws + L::O_DZA, L::NZP);
+        async_copy(sm.slot[0] + L::O_LXX, ws + L::STAGE + L::O_LXX, L::LXX + L::NXP);
+    }
     async_commit();
+    T imax = T(0), acc1 = T(0), acc2 = T(0);
     if (lane < NX) sm.cDx[lane] = T(0);
     for (int k = 0; k < N; k++) {
         T *wk = ws + (size_t)k * L::STAGE;
@@ -181,7 +189,10 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restric
         if (k + 1 < N) {
             T *nx = sm.slot[(k + 1) & 1];
             async_copy(nx, wk + L::STAGE, RUN1);
-            if (FINAL) async_copy(nx + L::O_LXX, wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP);
+            if (FINAL) {
+                async_copy(nx + L::O_DZA, wk + L::STAGE + L::O_DZA, L::NZP);
+                async_copy(nx + L::O_LXX, wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP);
+            }
             async_commit();
             async_wait<1>();
         } else {
@@ -215,6 +226,28 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restric
         if (lane < NZ) {
             wk[O_OUT + lane] = dz;
             sm.sDz[lane] = dz;
+        }
+        // box slacks / multipliers along this step (component `lane` of stage k)
+        if (var_kind<NX, NU>(k, lane, N).hasb) {
+            const T z = s[L::O_Z + lane], tl = s[L::O_TL + lane], tu = s[L::O_TU + lane];
+            const T ll = s[L::O_LL + lane], lu = s[L::O_LUP + lane], lb = s[L::O_LB + lane], ub = s[L::O_UB + lane];
+            const T itl = fast_rcp(tl), itu = fast_rcp(tu);
+            T rml = ll * tl, rmu = lu * tu;
+            if (FINAL) {
+                const BoxStep<T> a = box_step(z, s[L::O_DZA + lane], lb, ub, tl, tu, ll, lu, rml, rmu, itl, itu);
+                rml += a.dll * a.dtl - sigmu;
+                rmu += a.dlu * a.dtu - sigmu;
+            }
+            const BoxStep<T> b = box_step(z, dz, lb, ub, tl, tu, ll, lu, rml, rmu, itl, itu);
+            imax = fmax(imax, fmax(fmax(inv_ratio(b.dtl, itl), inv_ratio(b.dtu, itu)),
+                                   fmax(inv_ratio(b.dll, fast_rcp(ll)), inv_ratio(b.dlu, fast_rcp(lu)))));
+            if (!FINAL) {
+                acc1 += ll * b.dtl + tl * b.dll + lu * b.dtu + tu * b.dlu;
+                acc2 += b.dll * b.dtl + b.dlu * b.dtu;
+                // corrector gradient: (dl_a dt_a - sigma mu)/t_l - (du_a dtu_a - sigma mu)/t_u = c1 - sigma mu * c2
+                wk[L::O_C1 + lane] = b.dll * b.dtl * itl - b.dlu * b.dtu * itu;
+                wk[L::O_C2 + lane] = itl - itu;
+            }
         }
         warp_sync();
         // dx_{k+1} = rb_k + [B A] dz_k
@@ -263,6 +296,9 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restric
     // terminal stage: dz_N = [0; dx_N]
     if (lane < NZ) ws[(size_t)N * L::STAGE + O_OUT + lane] = (lane < NU) ? T(0) : sm.cDx[lane - NU];
     warp_sync();
+    imax_out = warp_max(imax);
+    acc1_out = warp_sum(acc1);
+    acc2_out = warp_sum(acc2);
 }
 
 // The whole QP solve for one instance.  On return the persistent iterate Xi/Ui has taken
@@ -279,7 +315,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
     const int N = P.N;
     const T thr0 = (T)P.ipm_thr0, mu0 = (T)P.ipm_mu0;
     const T nb = (T)(2 * NU * N + 2 * NX * (N - 1));
-    constexpr int FB = 4;  // stages per batch in the flat (elementwise) passes
+    constexpr int FB = 7;  // stages per batch in the flat update pass (all loads of a batch are in flight together)
     const T H0s = hess_diag<NX, NU, T>(P, 0, lane), H0N = hess_diag<NX, NU, T>(P, N, lane);  // stage / terminal weight of this lane
 
     for (int idx = lane; idx < NX * NX; idx += 32) sm.Lxx[idx] = T(0);
@@ -527,43 +563,17 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         // a breakdown (NaN) anywhere in the recursion propagates into the last pivot of stage 0
         if (!(last_sig == last_sig) || !(last_sig < T(HUGE_VAL))) { status = ST_QPFAIL; break; }
 
-        // ================= S2: forward sweep, affine step
-        forward_sweep<NX, NU, T, false>(P, sm, ws);
-
-        // ================= F2: affine step lengths, mu_aff, corrector gradient pieces
+        // ================= S2: forward sweep, affine step (+ its step length, mu_aff, corrector pieces)
         T a_aff, mu_aff, sigmu;
         {
-            T imax = T(0), acc1 = T(0), acc2 = T(0);
-            // stages are processed in batches: all loads of a batch are issued before any store,
-            // so a batch costs one memory round trip instead of one per stage
-            for (int k0 = 0; k0 < N; k0 += FB) {
-                BoxIn<T, FB> in;
-                load_box<NX, NU, T, FB, false>(in, ws, k0, N, N, lane);
-                MPCB_UNROLL
-                for (int u = 0; u < FB; u++) {
-                    if (!in.ok[u]) continue;
-                    T *wk = ws + (size_t)(k0 + u) * L::STAGE;
-                    const T tl = in.tl[u], tu = in.tu[u], ll = in.ll[u], lu = in.lu[u];
-                    const T itl = fast_rcp(tl), itu = fast_rcp(tu);
-                    const BoxStep<T> b = box_step(in.z[u], in.dza[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl, lu * tu, itl, itu);
-                    imax = fmax(imax, fmax(fmax(inv_ratio(b.dtl, itl), inv_ratio(b.dtu, itu)),
-                                           fmax(inv_ratio(b.dll, fast_rcp(ll)), inv_ratio(b.dlu, fast_rcp(lu)))));
-                    acc1 += ll * b.dtl + tl * b.dll + lu * b.dtu + tu * b.dlu;
-                    acc2 += b.dll * b.dtl + b.dlu * b.dtu;
-                    // corrector gradient: (dl_a dt_a - sigma mu)/t_l - (du_a dtu_a - sigma mu)/t_u = c1 - sigma mu * c2
-                    wk[L::O_C1 + lane] = b.dll * b.dtl * itl - b.dlu * b.dtu * itu;
-                    wk[L::O_C2 + lane] = itl - itu;
-                }
-            }
-            imax = warp_max(imax);
+            T imax, s1, s2;
+            forward_sweep<NX, NU, T, false>(P, sm, ws, T(0), imax, s1, s2);
             a_aff = (imax > T(1)) ? T(1) / imax : T(1);
-            const T s1 = warp_sum(acc1), s2 = warp_sum(acc2);
             mu_aff = (mu * nb + a_aff * s1 + a_aff * a_aff * s2) / nb;
             T sigma = mu_aff / mu;
             sigma = sigma * sigma * sigma;
             sigmu = sigma * mu;
         }
-        warp_sync();
 
         // ================= S3: backward sweep for the corrector increment (delta form)
         // record k: [BAt | Lu | invd | lvec] and [c1 c2]; pv_k is read-modify-written in global memory
@@ -607,29 +617,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             }
         }
 
-        // ================= S4: forward sweep, full predictor-corrector step (+ dpi)
-        forward_sweep<NX, NU, T, true>(P, sm, ws);
-
-        // ================= F4a: step length
+        // ================= S4: forward sweep, full predictor-corrector step (+ dpi, + step length)
         T alpha;
         {
-            T imax = T(0);
-            for (int k0 = 0; k0 < N; k0 += FB) {
-                BoxIn<T, FB> in;
-                load_box<NX, NU, T, FB, true>(in, ws, k0, N, N, lane);
-                MPCB_UNROLL
-                for (int u = 0; u < FB; u++) {
-                    if (!in.ok[u]) continue;
-                    const T tl = in.tl[u], tu = in.tu[u], ll = in.ll[u], lu = in.lu[u];
-                    const T itl = fast_rcp(tl), itu = fast_rcp(tu);
-                    const BoxStep<T> a = box_step(in.z[u], in.dza[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl, lu * tu, itl, itu);
-                    const BoxStep<T> b = box_step(in.z[u], in.dz[u], in.lb[u], in.ub[u], tl, tu, ll, lu, ll * tl + a.dll * a.dtl - sigmu,
-                                                  lu * tu + a.dlu * a.dtu - sigmu, itl, itu);
-                    imax = fmax(imax, fmax(fmax(inv_ratio(b.dtl, itl), inv_ratio(b.dtu, itu)),
-                                           fmax(inv_ratio(b.dll, fast_rcp(ll)), inv_ratio(b.dlu, fast_rcp(lu)))));
-                }
-            }
-            imax = warp_max(imax);
+            T imax, d1, d2;
+            forward_sweep<NX, NU, T, true>(P, sm, ws, sigmu, imax, d1, d2);
             // alpha = min(1, max(0.995, 1 - mu_aff) * alpha_max)
             const T tau = fmax(T(0.995), T(1) - mu_aff);
             alpha = (imax > tau) ? tau / imax : T(1);
