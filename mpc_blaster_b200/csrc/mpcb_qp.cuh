@@ -31,6 +31,7 @@ struct QpSmem {
     using L = Layout<NX, NU>;
     // every member is a multiple of 4 elements long, so all of them stay 32-byte aligned
     alignas(32) T slot[2][L::STAGE];
+    unsigned long long mbar[4];  // two mbarriers of the stage-prefetch pipeline (+ padding)
     T Lxx[L::LXX];       // factor of P_{k+1} (backward sweep), [NX][NX]; upper triangle stays zero
     T vrow[2][L::NXP];   // Householder pivot row broadcast (double buffered)
     T Lcol[L::NZ * L::NUP];  // first NU columns of the L_k being factorised, row-major [NZ][NUP]
@@ -165,8 +166,8 @@ MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
 // overlaps the latency of the recursion): the reciprocal of the largest admissible step `imax`,
 // and for the affine sweep the sums that give mu_aff(alpha) plus the corrector gradient pieces.
 template <int NX, int NU, typename T, bool FINAL>
-MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict__ ws, T sigmu, T &imax_out, T &acc1_out,
-                            T &acc2_out)
+MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, StagePipe &pipe, T *__restrict__ ws, T sigmu, T &imax_out,
+                            T &acc1_out, T &acc2_out)
 {
     using L = Layout<NX, NU>;
     constexpr int NZ = L::NZ;
@@ -175,12 +176,13 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restric
     const int N = P.N;
     // record k: [BAt | Lu | invd | lvec | rb | z tl tu ll lu lb ub]; FINAL: also [dza] and [Lxx | pv] of record k+1
     constexpr int RUN1 = L::O_G;
-    async_copy(sm.slot[0], ws, RUN1);
+    constexpr int TOTAL = RUN1 + (FINAL ? L::NZP + L::LXX + L::NXP : 0);
+    pipe_expect(pipe, 0, TOTAL);
+    pipe_copy(pipe, 0, sm.slot[0], ws, RUN1);
     if (FINAL) {
-        async_copy(sm.slot[0] + L::O_DZA, ws + L::O_DZA, L::NZP);
-        async_copy(sm.slot[0] + L::O_LXX, ws + L::STAGE + L::O_LXX, L::LXX + L::NXP);
+        pipe_copy(pipe, 0, sm.slot[0] + L::O_DZA, ws + L::O_DZA, L::NZP);
+        pipe_copy(pipe, 0, sm.slot[0] + L::O_LXX, ws + L::STAGE + L::O_LXX, L::LXX + L::NXP);
     }
-    async_commit();
     T imax = T(0), acc1 = T(0), acc2 = T(0);
     if (lane < NX) sm.cDx[lane] = T(0);
     for (int k = 0; k < N; k++) {
@@ -188,16 +190,14 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restric
         const T *s = sm.slot[k & 1];
         if (k + 1 < N) {
             T *nx = sm.slot[(k + 1) & 1];
-            async_copy(nx, wk + L::STAGE, RUN1);
+            pipe_expect(pipe, (k + 1) & 1, TOTAL);
+            pipe_copy(pipe, (k + 1) & 1, nx, wk + L::STAGE, RUN1);
             if (FINAL) {
-                async_copy(nx + L::O_DZA, wk + L::STAGE + L::O_DZA, L::NZP);
-                async_copy(nx + L::O_LXX, wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP);
+                pipe_copy(pipe, (k + 1) & 1, nx + L::O_DZA, wk + L::STAGE + L::O_DZA, L::NZP);
+                pipe_copy(pipe, (k + 1) & 1, nx + L::O_LXX, wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP);
             }
-            async_commit();
-            async_wait<1>();
-        } else {
-            async_wait<0>();
         }
+        pipe_wait(pipe, k & 1);
         warp_sync();
         // du = -Luu^{-T} (lvec + Lxu' dx)
         T yy = T(0);
@@ -295,6 +295,7 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, T *__restric
     }
     // terminal stage: dz_N = [0; dx_N]
     if (lane < NZ) ws[(size_t)N * L::STAGE + O_OUT + lane] = (lane < NU) ? T(0) : sm.cDx[lane - NU];
+    pipe_fence();
     warp_sync();
     imax_out = warp_max(imax);
     acc1_out = warp_sum(acc1);
@@ -319,6 +320,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
     const T H0s = hess_diag<NX, NU, T>(P, 0, lane), H0N = hess_diag<NX, NU, T>(P, N, lane);  // stage / terminal weight of this lane
 
     for (int idx = lane; idx < NX * NX; idx += 32) sm.Lxx[idx] = T(0);
+    StagePipe pipe;
+    pipe_init(pipe, sm.mbar);
 
     // ---------------- F0: QP data and cold start [upstream D8]: z = 0 (dx_0 pinned), pi = 0,
     // t >= slack floor, lam = mu0/t.  Cost gradient and bounds on the increments.
@@ -372,6 +375,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
     T est_g = warp_max(eg), est_b = warp_max(eb), est_d = warp_max(ed);
     T comp = mu0, mu = mu0;
     int status = ST_MAXITER, it = 0;
+    pipe_fence();  // the QP data written above is fetched by the bulk-copy pipeline below
     warp_sync();
 
     for (it = 0; it < P.ipm_max_iter; it++) {
@@ -387,9 +391,9 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         {
             // terminal stage N: no inputs, no bounds; L_N = sqrt(Q_t), p_N = q_N
             T *wN = ws + (size_t)N * L::STAGE;
-            async_copy(sm.slot[(N - 1) & 1], wN - L::STAGE, L::BAT);
-            async_copy(sm.slot[(N - 1) & 1] + L::O_Z, wN - L::STAGE + L::O_Z, RUNB);
-            async_commit();
+            pipe_expect(pipe, (N - 1) & 1, L::BAT + RUNB);
+            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1], wN - L::STAGE, L::BAT);
+            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1] + L::O_Z, wN - L::STAGE + L::O_Z, RUNB);
             if (lane >= NU && lane < NZ) {
                 const int i = lane - NU;
                 const T H0 = H0N;
@@ -412,13 +416,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             const T *s = sm.slot[k & 1];
             if (k > 0) {
                 T *nx = sm.slot[(k - 1) & 1];
-                async_copy(nx, wk - L::STAGE, L::BAT);
-                async_copy(nx + L::O_Z, wk - L::STAGE + L::O_Z, RUNB);
-                async_commit();
-                async_wait<1>();
-            } else {
-                async_wait<0>();
+                pipe_expect(pipe, (k - 1) & 1, L::BAT + RUNB);
+                pipe_copy(pipe, (k - 1) & 1, nx, wk - L::STAGE, L::BAT);
+                pipe_copy(pipe, (k - 1) & 1, nx + L::O_Z, wk - L::STAGE + L::O_Z, RUNB);
             }
+            pipe_wait(pipe, k & 1);
             warp_sync();
             const int jr = lane < NZ ? lane : 0;
             T brow[NX];
@@ -560,6 +562,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             if (k > 0)
                 for (int idx = lane; idx < NX * NX; idx += 32) wk[L::O_LXX + idx] = sm.Lxx[idx];
         }
+        pipe_fence();  // L, lvec, r_b, p written by this sweep are fetched by the next ones
+        warp_sync();
         // a breakdown (NaN) anywhere in the recursion propagates into the last pivot of stage 0
         if (!(last_sig == last_sig) || !(last_sig < T(HUGE_VAL))) { status = ST_QPFAIL; break; }
 
@@ -567,7 +571,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         T a_aff, mu_aff, sigmu;
         {
             T imax, s1, s2;
-            forward_sweep<NX, NU, T, false>(P, sm, ws, T(0), imax, s1, s2);
+            forward_sweep<NX, NU, T, false>(P, sm, pipe, ws, T(0), imax, s1, s2);
             a_aff = (imax > T(1)) ? T(1) / imax : T(1);
             mu_aff = (mu * nb + a_aff * s1 + a_aff * a_aff * s2) / nb;
             T sigma = mu_aff / mu;
@@ -579,9 +583,9 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         // record k: [BAt | Lu | invd | lvec] and [c1 c2]; pv_k is read-modify-written in global memory
         {
             constexpr int RUN1 = L::O_RB;
-            async_copy(sm.slot[(N - 1) & 1], ws + (size_t)(N - 1) * L::STAGE, RUN1);
-            async_copy(sm.slot[(N - 1) & 1] + L::O_C1, ws + (size_t)(N - 1) * L::STAGE + L::O_C1, 2 * L::NZP);
-            async_commit();
+            pipe_expect(pipe, (N - 1) & 1, RUN1 + 2 * L::NZP);
+            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1], ws + (size_t)(N - 1) * L::STAGE, RUN1);
+            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1] + L::O_C1, ws + (size_t)(N - 1) * L::STAGE + L::O_C1, 2 * L::NZP);
             if (lane < NX) sm.cPv[lane] = T(0);
             for (int k = N - 1; k >= 0; k--) {
                 T *wk = ws + (size_t)k * L::STAGE;
@@ -589,13 +593,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
                 const T pv_old = (lane >= NU && lane < NZ) ? wk[L::O_PV + lane - NU] : T(0);
                 if (k > 0) {
                     T *nx = sm.slot[(k - 1) & 1];
-                    async_copy(nx, wk - L::STAGE, RUN1);
-                    async_copy(nx + L::O_C1, wk - L::STAGE + L::O_C1, 2 * L::NZP);
-                    async_commit();
-                    async_wait<1>();
-                } else {
-                    async_wait<0>();
+                    pipe_expect(pipe, (k - 1) & 1, RUN1 + 2 * L::NZP);
+                    pipe_copy(pipe, (k - 1) & 1, nx, wk - L::STAGE, RUN1);
+                    pipe_copy(pipe, (k - 1) & 1, nx + L::O_C1, wk - L::STAGE + L::O_C1, 2 * L::NZP);
                 }
+                pipe_wait(pipe, k & 1);
                 warp_sync();
                 const int jr = lane < NZ ? lane : 0;
                 const VarKind vk = var_kind<NX, NU>(k, lane, N);
@@ -615,13 +617,15 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
                 else if (lane < NZ) { wk[L::O_PV + lane - NU] = pv_old + l; sm.cPv[lane - NU] = l; }
                 warp_sync();
             }
+            pipe_fence();
+            warp_sync();
         }
 
         // ================= S4: forward sweep, full predictor-corrector step (+ dpi, + step length)
         T alpha;
         {
             T imax, d1, d2;
-            forward_sweep<NX, NU, T, true>(P, sm, ws, sigmu, imax, d1, d2);
+            forward_sweep<NX, NU, T, true>(P, sm, pipe, ws, sigmu, imax, d1, d2);
             // alpha = min(1, max(0.995, 1 - mu_aff) * alpha_max)
             const T tau = fmax(T(0.995), T(1) - mu_aff);
             alpha = (imax > tau) ? tau / imax : T(1);
@@ -668,6 +672,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         est_g *= (T(1) - alpha);
         est_b *= (T(1) - alpha);
         est_d *= (T(1) - alpha);
+        pipe_fence();
         warp_sync();
         if (!(alpha >= (T)P.alpha_min)) {
             status = (alpha == alpha) ? ST_MINSTEP : ST_NAN;
