@@ -236,6 +236,27 @@ def run_gpu(args):
     e2e_t = float(e2e_all.item())
     assert np.array_equal(u0_h, u0.cpu().numpy()), "host path and device path disagree"
 
+    # ---- the QUAD12 instantiation (12 states / 4 inputs, north_star's sizing) on the same scenario, N=1 only
+    quad12 = None
+    if world == 1 and not args.no_quad12:
+        q = BlasterMPC.canonical(N=N, batch=B, variant=12)
+        qx_h, qy_h, qt_h = workload(rank, B, 12)
+        qx, qy, qt = (torch.as_tensor(a, device=dev) for a in (qx_h, qy_h, qt_h))
+        qms = []
+        for i in range(args.warmup + max(5, args.steps // 3)):
+            q.reset(qx, qt)
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _, _, _, qst = q.solve(qx, qy, want_traj=False)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= args.warmup:
+                qms.append(a.elapsed_time(b))
+        quad12 = {"value": B / (float(np.mean(qms)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(qms)),
+                  "mean_ipm_iters": float(q.iters.double().mean().item()), "converged_frac": float((qst == 0).double().mean().item())}
+        del q
+
     # ---- final result gather (the only collective of the job)
     if world > 1:
         from mpc_blaster_b200.scheduler import gather_batch
@@ -297,7 +318,7 @@ def run_gpu(args):
                      "algorithmic_mflop_per_solve": flops / 1e6},
             "solver": {"mean_ipm_iters": iters_mean, "converged_frac": ok_frac,
                        "p50_ms": float(np.percentile(step_ms, 50)), "p99_ms": float(np.percentile(step_ms, 99))},
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "quad12": quad12}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -312,6 +333,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-quad12", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "graft" else args.warmup
     if args.impl == "reference":

@@ -322,3 +322,51 @@ def test_from_acados_json_equals_canonical(cuda_device):
     b = _mpc(20, B)
     for s, t in zip(a.solve(x0, yref), b.solve(x0, yref)):
         assert torch.equal(s, t)
+
+
+@pytest.mark.parametrize("variant,N,B", [(17, 2, 3), (12, 3, 5), (17, 80, 8), (17, 7, 33)])
+def test_edge_shapes(cuda_device, variant, N, B):
+    """Shortest horizons (N=2: no stage carries state bounds beyond k=1), the longest one of
+    BASELINE.json (N=80), odd batch sizes."""
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.closed_loop_setpoints(B, seed=9, nx=P.nx, nu=P.nu)
+    mpc = _mpc(N, B, variant)
+    orc = co.BatchRTI(P, B)
+    trim = sc.hover_trim(P.nu)
+    mpc.reset(x0, trim)
+    orc.reset(x0, trim)
+    u0, X, U, st = mpc.solve(x0, yref)
+    uo, Xo, Uo, sto = orc.solve(x0, yref)
+    assert (st.cpu().numpy() == sto).all()
+    ok = sto == 0
+    assert ok.mean() >= 0.8
+    assert (mpc.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
+    assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+
+
+def test_api_misuse_is_reported_not_crashed(cuda_device):
+    from mpc_blaster_b200.solver import MpcbError
+    mpc = _mpc(5, 4)
+    x0, yref = sc.random_setpoints(8, seed=1)
+    with pytest.raises(MpcbError):
+        mpc.solve(x0, yref)            # batch 8 > max_batch 4
+    with pytest.raises(ValueError):
+        mpc.solve(x0[:4], yref[:3])    # yref batch mismatch
+    with pytest.raises(ValueError):
+        mpc.solve(x0[:4, :5], yref[:4])
+    u0, X, U, st = mpc.solve(x0[:4], yref[:4])  # still usable afterwards
+    assert int((st == 0).sum()) == 4
+
+
+def test_million_instance_chunking_smoke(cuda_device):
+    """Config 5 scale check (reduced): 200k instances through a workspace of 32k instances --
+    chunk boundaries must not change results (compare the first and last chunk against a fresh solver)."""
+    B, N, C = 200_000, 20, 32_768
+    x0, yref = sc.random_setpoints(B, seed=4567)
+    big = _mpc(N, B, ws_batch=C)
+    u0, _, _, st = big.solve(x0, yref, want_traj=False)
+    assert float((st == 0).double().mean()) > 0.99
+    for lo in (0, B - 1000):
+        small = _mpc(N, 1000)
+        us, _, _, ss = small.solve(x0[lo:lo + 1000], yref[lo:lo + 1000], want_traj=False)
+        assert torch.equal(us, u0[lo:lo + 1000]) and torch.equal(ss, st[lo:lo + 1000])

@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""Small end-to-end case for compute-sanitizer (memcheck / racecheck): 8 instances, N=6, both
+model variants, one solve each plus plant step, cost and command map."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpc_blaster_b200 import BlasterMPC, scenarios as sc  # noqa: E402
+
+for variant in (17, 12):
+    nx, nu = (17, 6) if variant == 17 else (12, 4)
+    x0, yref = sc.random_setpoints(8, seed=3, nx=nx, nu=nu)
+    mpc = BlasterMPC.canonical(N=6, batch=8, variant=variant)
+    mpc.reset(x0, sc.hover_trim(nu))
+    u0, X, U, st = mpc.solve(x0, yref)
+    xn = mpc.step_plant(x0, u0)
+    c = mpc.cost(yref)
+    q, t = mpc.command_map(X[:, 0], u0) if variant == 17 else (None, None)
+    torch.cuda.synchronize()
+    print(variant, st.tolist(), mpc.iters.tolist(), float(c.sum()))
+print("done")
