@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -47,8 +48,11 @@ __global__ void __launch_bounds__(128) linearize_kernel(const __grid_constant__ 
 }
 
 // K2: one warp per instance -- IPM/Riccati QP solve + RTI update.
-template <int NX, int NU, int WPB>
-__global__ void __launch_bounds__(32 * WPB) qp_kernel(const __grid_constant__ Params P, double *__restrict__ X,
+// NSLOT = 2 / MINB = 1: latency variant (stage prefetch, all the registers it wants);
+// NSLOT = 1 / MINB = 12: throughput variant the host scheduler picks for chunks of many waves
+// (16 KB of shared memory and <= 168 registers per warp -> 12 warps per SM instead of 9).
+template <int NX, int NU, int WPB, int NSLOT, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) qp_kernel(const __grid_constant__ Params P, double *__restrict__ X,
                                                       double *__restrict__ U, const double *__restrict__ x0,
                                                       const double *__restrict__ yref, int yref_mode,
                                                       double *__restrict__ ws, double *__restrict__ u0,
@@ -56,8 +60,8 @@ __global__ void __launch_bounds__(32 * WPB) qp_kernel(const __grid_constant__ Pa
                                                       int inst0, int B)
 {
     using L = Layout<NX, NU>;
-    __shared__ __align__(16) QpSmem<NX, NU, double> sm_arr[WPB];
-    QpSmem<NX, NU, double> *sm = &sm_arr[threadIdx.x >> 5];
+    __shared__ __align__(16) QpSmem<NX, NU, double, NSLOT> sm_arr[WPB];
+    QpSmem<NX, NU, double, NSLOT> *sm = &sm_arr[threadIdx.x >> 5];
     const int N = P.N;
     const int li = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (li >= B) return;
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(32 * WPB) qp_kernel(const __grid_constant__ Pa
     if (yref_mode == MPCB_PER_INSTANCE) yr = yref + (size_t)inst * (NX + NU);
     if (yref_mode == MPCB_PER_STAGE) yr = yref + (size_t)inst * (N + 1) * (NX + NU);
     int it = 0;
-    const int st = qp_solve_warp<NX, NU, double>(P, *sm, ws + (size_t)li * L::instance_stride(N), Xi, Ui,
+    const int st = qp_solve_warp<NX, NU, double, NSLOT>(P, *sm, ws + (size_t)li * L::instance_stride(N), Xi, Ui,
                                                  x0 + (size_t)inst * NX, yr, yref_mode == MPCB_PER_STAGE, &it);
     const int lane = threadIdx.x & 31;
     if (lane == 0) {
@@ -229,6 +233,7 @@ struct mpcb_handle {
     double *d_stage = nullptr;
     size_t d_stage_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    int throughput_batch = 1 << 30;  // chunks at least this large use the high-occupancy QP kernel variant
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around K1 and K2 of the last solve (profiling)
     bool profile = false;
     std::string err;
@@ -291,7 +296,7 @@ template <int NX, int NU>
 int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
                         double *u0, int32_t *status, int32_t *iters, int B, cudaStream_t s)
 {
-    static_assert(sizeof(QpSmem<NX, NU, double>) * kWPB <= 48 * 1024, "static shared memory limit");
+    static_assert(sizeof(QpSmem<NX, NU, double, 2>) * kWPB <= 48 * 1024, "static shared memory limit");
     const size_t smem = 0;
     for (int i0 = 0; i0 < B; i0 += h->ws_batch) {
         const int nb = (B - i0 < h->ws_batch) ? B - i0 : h->ws_batch;
@@ -301,8 +306,12 @@ int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, in
         if (prof) cudaEventRecord(h->ev[0], s);
         linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
         if (prof) cudaEventRecord(h->ev[1], s);
-        qp_kernel<NX, NU, kWPB><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws,
-                                                                                  u0, status, iters, i0, nb);
+        if (nb >= h->throughput_batch)
+            qp_kernel<NX, NU, kWPB, 1, 12><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+                                                                                             h->ws, u0, status, iters, i0, nb);
+        else
+            qp_kernel<NX, NU, kWPB, 2, 1><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+                                                                                            h->ws, u0, status, iters, i0, nb);
         if (prof) cudaEventRecord(h->ev[2], s);
         g_launches += 2;
     }
@@ -381,6 +390,11 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     }
     if (wsb > h->max_batch) wsb = h->max_batch;
     h->ws_batch = wsb;
+    {
+        // more than ~2 waves of the latency variant (9 warps x 148 SMs): switch to the throughput variant
+        const char *tb = getenv("MPCB_THROUGHPUT_BATCH");
+        h->throughput_batch = tb ? atoi(tb) : 4096;
+    }
     const size_t B = (size_t)h->max_batch;
     const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;
 #define ALLOC(ptr, bytes)                                                                   \

@@ -26,11 +26,14 @@ namespace mpcb {
 
 // Per-warp shared memory: two stage-record images (same offsets as the global record) plus
 // the data that is carried from one stage of a sweep to the next.
-template <int NX, int NU, typename T>
+// NSLOT = 2: the next stage's record is prefetched while the current one is processed (latency
+// variant, 25 KB per warp); NSLOT = 1: one buffer, fetched at the top of each stage (throughput
+// variant for batches of many waves: 16 KB per warp, so more warps per SM hide the latency instead).
+template <int NX, int NU, typename T, int NSLOT = 2>
 struct QpSmem {
     using L = Layout<NX, NU>;
     // every member is a multiple of 4 elements long, so all of them stay 32-byte aligned
-    alignas(32) T slot[2][L::STAGE];
+    alignas(32) T slot[NSLOT][L::STAGE];
     unsigned long long mbar[4];  // two mbarriers of the stage-prefetch pipeline (+ padding)
     T Lxx[L::LXX];       // factor of P_{k+1} (backward sweep), [NX][NX]; upper triangle stays zero
     T vrow[2][L::NXP];   // Householder pivot row broadcast (double buffered)
@@ -119,8 +122,8 @@ MPCB_DEV void load_box(BoxIn<T, FBN> &in, const T *__restrict__ ws, int k0, int 
 
 // t2 = P r + p with P = Lxx Lxx' (Lxx in shared memory, zero upper triangle);
 // r in sm.sRb, p in sm.cPv, result in sm.sT2.
-template <int NX, int NU, typename T>
-MPCB_DEV void apply_P(QpSmem<NX, NU, T> &sm)
+template <int NX, int NU, typename T, int NSLOT>
+MPCB_DEV void apply_P(QpSmem<NX, NU, T, NSLOT> &sm)
 {
     const int lane = lane_id();
     const int c = lane < NX ? lane : 0;
@@ -165,8 +168,8 @@ MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
 // The elementwise box work of the step just computed is folded in (it only depends on dz_k and
 // overlaps the latency of the recursion): the reciprocal of the largest admissible step `imax`,
 // and for the affine sweep the sums that give mu_aff(alpha) plus the corrector gradient pieces.
-template <int NX, int NU, typename T, bool FINAL>
-MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, StagePipe &pipe, T *__restrict__ ws, T sigmu, T &imax_out,
+template <int NX, int NU, typename T, int NSLOT, bool FINAL>
+MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, StagePipe &pipe, T *__restrict__ ws, T sigmu, T &imax_out,
                             T &acc1_out, T &acc2_out)
 {
     using L = Layout<NX, NU>;
@@ -177,27 +180,29 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, StagePipe &p
     // record k: [BAt | Lu | invd | lvec | rb | z tl tu ll lu lb ub]; FINAL: also [dza] and [Lxx | pv] of record k+1
     constexpr int RUN1 = L::O_G;
     constexpr int TOTAL = RUN1 + (FINAL ? L::NZP + L::LXX + L::NXP : 0);
-    pipe_expect(pipe, 0, TOTAL);
-    pipe_copy(pipe, 0, sm.slot[0], ws, RUN1);
-    if (FINAL) {
-        pipe_copy(pipe, 0, sm.slot[0] + L::O_DZA, ws + L::O_DZA, L::NZP);
-        pipe_copy(pipe, 0, sm.slot[0] + L::O_LXX, ws + L::STAGE + L::O_LXX, L::LXX + L::NXP);
-    }
+    auto fetch = [&](int k, int half) {
+        const T *wk = ws + (size_t)k * L::STAGE;
+        T *dst = sm.slot[half];
+        pipe_expect(pipe, half, TOTAL);
+        pipe_copy(pipe, half, dst, wk, RUN1);
+        if (FINAL) {
+            pipe_copy(pipe, half, dst + L::O_DZA, wk + L::O_DZA, L::NZP);
+            pipe_copy(pipe, half, dst + L::O_LXX, wk + L::STAGE + L::O_LXX, L::LXX + L::NXP);
+        }
+    };
+    if (NSLOT == 2) fetch(0, 0);
     T imax = T(0), acc1 = T(0), acc2 = T(0);
     if (lane < NX) sm.cDx[lane] = T(0);
     for (int k = 0; k < N; k++) {
         T *wk = ws + (size_t)k * L::STAGE;
-        const T *s = sm.slot[k & 1];
-        if (k + 1 < N) {
-            T *nx = sm.slot[(k + 1) & 1];
-            pipe_expect(pipe, (k + 1) & 1, TOTAL);
-            pipe_copy(pipe, (k + 1) & 1, nx, wk + L::STAGE, RUN1);
-            if (FINAL) {
-                pipe_copy(pipe, (k + 1) & 1, nx + L::O_DZA, wk + L::STAGE + L::O_DZA, L::NZP);
-                pipe_copy(pipe, (k + 1) & 1, nx + L::O_LXX, wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP);
-            }
+        const int half = (NSLOT == 2) ? (k & 1) : 0;
+        const T *s = sm.slot[half];
+        if (NSLOT == 2) {
+            if (k + 1 < N) fetch(k + 1, (k + 1) & 1);
+        } else {
+            fetch(k, 0);
         }
-        pipe_wait(pipe, k & 1);
+        pipe_wait(pipe, half);
         warp_sync();
         // du = -Luu^{-T} (lvec + Lxu' dx)
         T yy = T(0);
@@ -305,8 +310,8 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T> &sm, StagePipe &p
 // The whole QP solve for one instance.  On return the persistent iterate Xi/Ui has taken
 // the full step (FIXED_STEP, step length 1.0: acados_ocp_blasterModel.json globalization /
 // nlp_solver_step_length).  Returns the status; *iters_out = IPM iterations.
-template <int NX, int NU, typename T>
-MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict__ ws, T *__restrict__ Xi,
+template <int NX, int NU, typename T, int NSLOT>
+MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__restrict__ ws, T *__restrict__ Xi,
                            T *__restrict__ Ui, const T *__restrict__ x0, const T *__restrict__ yref, int yps,
                            int *iters_out)
 {
@@ -388,12 +393,16 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         // record k: run A = [BAt], run B = [z tl tu ll lu lb ub g pi b]
         constexpr int RUNB = L::O_C1 - L::O_Z;
         T last_sig = T(1);
+        auto fetch1 = [&](int k, int half) {
+            const T *wk = ws + (size_t)k * L::STAGE;
+            pipe_expect(pipe, half, L::BAT + RUNB);
+            pipe_copy(pipe, half, sm.slot[half], wk, L::BAT);
+            pipe_copy(pipe, half, sm.slot[half] + L::O_Z, wk + L::O_Z, RUNB);
+        };
         {
             // terminal stage N: no inputs, no bounds; L_N = sqrt(Q_t), p_N = q_N
             T *wN = ws + (size_t)N * L::STAGE;
-            pipe_expect(pipe, (N - 1) & 1, L::BAT + RUNB);
-            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1], wN - L::STAGE, L::BAT);
-            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1] + L::O_Z, wN - L::STAGE + L::O_Z, RUNB);
+            if (NSLOT == 2) fetch1(N - 1, (N - 1) & 1);
             if (lane >= NU && lane < NZ) {
                 const int i = lane - NU;
                 const T H0 = H0N;
@@ -413,14 +422,14 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         }
         for (int k = N - 1; k >= 0; k--) {
             T *wk = ws + (size_t)k * L::STAGE;
-            const T *s = sm.slot[k & 1];
-            if (k > 0) {
-                T *nx = sm.slot[(k - 1) & 1];
-                pipe_expect(pipe, (k - 1) & 1, L::BAT + RUNB);
-                pipe_copy(pipe, (k - 1) & 1, nx, wk - L::STAGE, L::BAT);
-                pipe_copy(pipe, (k - 1) & 1, nx + L::O_Z, wk - L::STAGE + L::O_Z, RUNB);
+            const int half = (NSLOT == 2) ? (k & 1) : 0;
+            const T *s = sm.slot[half];
+            if (NSLOT == 2) {
+                if (k > 0) fetch1(k - 1, (k - 1) & 1);
+            } else {
+                fetch1(k, 0);
             }
-            pipe_wait(pipe, k & 1);
+            pipe_wait(pipe, half);
             warp_sync();
             const int jr = lane < NZ ? lane : 0;
             T brow[NX];
@@ -466,7 +475,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
             }
             warp_sync();
             // t2 = P_{k+1} r_k + p_{k+1}
-            apply_P<NX, NU, T>(sm);
+            apply_P<NX, NU, T, NSLOT>(sm);
             // carry this stage's pi and dx-part of z to stage k-1 (cPi / cZx were consumed above)
             if (lane < NX) { sm.cPi[lane] = s[L::O_PI + lane]; sm.cZx[lane] = s[L::O_Z + NU + lane]; }
             // W = [B A]' Lxx_{k+1}   (row `lane`)
@@ -571,7 +580,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         T a_aff, mu_aff, sigmu;
         {
             T imax, s1, s2;
-            forward_sweep<NX, NU, T, false>(P, sm, pipe, ws, T(0), imax, s1, s2);
+            forward_sweep<NX, NU, T, NSLOT, false>(P, sm, pipe, ws, T(0), imax, s1, s2);
             a_aff = (imax > T(1)) ? T(1) / imax : T(1);
             mu_aff = (mu * nb + a_aff * s1 + a_aff * a_aff * s2) / nb;
             T sigma = mu_aff / mu;
@@ -583,21 +592,25 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         // record k: [BAt | Lu | invd | lvec] and [c1 c2]; pv_k is read-modify-written in global memory
         {
             constexpr int RUN1 = L::O_RB;
-            pipe_expect(pipe, (N - 1) & 1, RUN1 + 2 * L::NZP);
-            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1], ws + (size_t)(N - 1) * L::STAGE, RUN1);
-            pipe_copy(pipe, (N - 1) & 1, sm.slot[(N - 1) & 1] + L::O_C1, ws + (size_t)(N - 1) * L::STAGE + L::O_C1, 2 * L::NZP);
+            auto fetch3 = [&](int k, int half) {
+                const T *wk = ws + (size_t)k * L::STAGE;
+                pipe_expect(pipe, half, RUN1 + 2 * L::NZP);
+                pipe_copy(pipe, half, sm.slot[half], wk, RUN1);
+                pipe_copy(pipe, half, sm.slot[half] + L::O_C1, wk + L::O_C1, 2 * L::NZP);
+            };
+            if (NSLOT == 2) fetch3(N - 1, (N - 1) & 1);
             if (lane < NX) sm.cPv[lane] = T(0);
             for (int k = N - 1; k >= 0; k--) {
                 T *wk = ws + (size_t)k * L::STAGE;
-                const T *s = sm.slot[k & 1];
+                const int half = (NSLOT == 2) ? (k & 1) : 0;
+                const T *s = sm.slot[half];
                 const T pv_old = (lane >= NU && lane < NZ) ? wk[L::O_PV + lane - NU] : T(0);
-                if (k > 0) {
-                    T *nx = sm.slot[(k - 1) & 1];
-                    pipe_expect(pipe, (k - 1) & 1, RUN1 + 2 * L::NZP);
-                    pipe_copy(pipe, (k - 1) & 1, nx, wk - L::STAGE, RUN1);
-                    pipe_copy(pipe, (k - 1) & 1, nx + L::O_C1, wk - L::STAGE + L::O_C1, 2 * L::NZP);
+                if (NSLOT == 2) {
+                    if (k > 0) fetch3(k - 1, (k - 1) & 1);
+                } else {
+                    fetch3(k, 0);
                 }
-                pipe_wait(pipe, k & 1);
+                pipe_wait(pipe, half);
                 warp_sync();
                 const int jr = lane < NZ ? lane : 0;
                 const VarKind vk = var_kind<NX, NU>(k, lane, N);
@@ -625,7 +638,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T> &sm, T *__restrict
         T alpha;
         {
             T imax, d1, d2;
-            forward_sweep<NX, NU, T, true>(P, sm, pipe, ws, sigmu, imax, d1, d2);
+            forward_sweep<NX, NU, T, NSLOT, true>(P, sm, pipe, ws, sigmu, imax, d1, d2);
             // alpha = min(1, max(0.995, 1 - mu_aff) * alpha_max)
             const T tau = fmax(T(0.995), T(1) - mu_aff);
             alpha = (imax > tau) ? tau / imax : T(1);

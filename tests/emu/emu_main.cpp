@@ -4,6 +4,7 @@
 // that tests/test_kernel_emulation.py can check the kernel logic against the oracle
 // without a GPU.  Never part of the product library.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -13,7 +14,7 @@
 
 using namespace mpcb;
 
-template <int NX, int NU>
+template <int NX, int NU, int NSLOT>
 static int rti_one(const Params &P, double *X, double *U, const double *x0, const double *yref, int yps, const double *p,
                    int p_per_stage, int *iters, double *BAt_out, double *b_out)
 {
@@ -32,11 +33,11 @@ static int rti_one(const Params &P, double *X, double *U, const double *x0, cons
         if (b_out) memcpy(b_out + (size_t)k * NX, ws.data() + (size_t)k * L::STAGE + L::O_B, sizeof(double) * NX);
     }
     int status = -1, it = 0;
-    QpSmem<NX, NU, double> sm;
+    QpSmem<NX, NU, double, NSLOT> sm;
     memset(&sm, 0, sizeof(sm));
     emu::run_warp([&]() {
         int my_it = 0;
-        int st = qp_solve_warp<NX, NU, double>(P, sm, ws.data(), X, U, x0, yref, yps, &my_it);
+        int st = qp_solve_warp<NX, NU, double, NSLOT>(P, sm, ws.data(), X, U, x0, yref, yps, &my_it);
         if (emu::lane() == 0) { status = st; it = my_it; }
     });
     *iters = it;
@@ -50,8 +51,14 @@ size_t emu_params_size() { return sizeof(Params); }
 int emu_rti_solve(const Params *P, double *X, double *U, const double *x0, const double *yref, int yps, const double *p,
                   int p_per_stage, int *iters, double *BAt_out, double *b_out)
 {
-    if (P->variant == 17) return rti_one<17, 6>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
-    return rti_one<12, 4>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+    // MPCB_EMU_NSLOT=1 exercises the single-buffer (throughput) variant
+    const char *ns = getenv("MPCB_EMU_NSLOT");
+    const bool one = ns && ns[0] == '1';
+    if (P->variant == 17)
+        return one ? rti_one<17, 6, 1>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out)
+                   : rti_one<17, 6, 2>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+    return one ? rti_one<12, 4, 1>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out)
+               : rti_one<12, 4, 2>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
 }
 
 void emu_plant_step(const Params *P, const double *x, const double *u, const double *p, double *xn)
