@@ -39,6 +39,14 @@ typedef struct {
 
 #define GRAV 9.81 /* blastermodel.py:93 */
 
+/* ORC_DEBUG=1 prints the IPM residual history (read once, not in the timed loop) */
+static int orc_debug(void)
+{
+    static int flag = -1;
+    if (flag < 0) flag = getenv("ORC_DEBUG") != NULL;
+    return flag;
+}
+
 /* blastermodel.py:124,162-167: full 17-state model */
 static void orc_f17(const orc_problem *P, const double *x, const double *u, const double *p, double *xd)
 {

@@ -380,12 +380,12 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
         /* the three linear residuals are affine in the iterate and everything takes the same
          * step, so each shrinks by exactly (1-alpha); the stopping test uses those values */
         if (P->rg_mode == 2) { res_g = rg_est; res_b = rb_est; res_d = rd_est; }
-        if (getenv("ORC_DEBUG")) fprintf(stderr, "it %d res_g %.3e res_b %.3e res_d %.3e comp %.3e mu %.3e\n", it, res_g, res_b, res_d, comp, mu);
+        if (orc_debug()) fprintf(stderr, "it %d res_g %.3e res_b %.3e res_d %.3e comp %.3e mu %.3e\n", it, res_g, res_b, res_d, comp, mu);
         if (!(res_g == res_g) || !(res_b == res_b) || !(mu == mu)) { status = 1; break; }
         if (res_g <= P->tol_stat && res_b <= P->tol_eq && res_d <= P->tol_ineq && comp <= P->tol_comp) { status = 0; break; }
         /* factorise with barrier diagonal */
         for (size_t i = 0; i < n; i++) w->Hd[i] = w->H0[i] + w->ll[i] / w->tl[i] + w->lu[i] / w->tu[i];
-        if (getenv("ORC_DEBUG")) {
+        if (orc_debug()) {
             double gmax = 0, gxmax = 0;
             for (size_t i = 0; i < n; i++) { double gm = w->Hd[i] - w->H0[i]; if (gm > gmax) gmax = gm; if ((int)(i % NZ) >= NU && gm > gxmax) gxmax = gm; }
             fprintf(stderr, "   barrier max %.3e  (states %.3e)\n", gmax, gxmax);
