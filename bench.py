@@ -327,8 +327,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-steps", type=int, default=20)

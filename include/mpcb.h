@@ -36,6 +36,8 @@ extern "C" {
 #define MPCB_VARIANT_BLASTER17 17 /* the reference's model: 17 states / 6 inputs / 25 params */
 #define MPCB_VARIANT_QUAD12 12    /* states 0..11, inputs 0..3, gimbal frozen (north_star sizing) */
 #define MPCB_NP 25
+#define MPCB_F64 64
+#define MPCB_F32 32
 
 /* yref_mode / p_mode */
 #define MPCB_SHARED 0       /* one vector for every instance and stage: yref[ny] / p[25]      */
@@ -57,6 +59,7 @@ typedef struct mpcb_config {
     double ipm_mu0;       /* initial lam*t of every bound (cold start) */
     double ipm_thr0;      /* initial slack floor: >= 0 absolute, < 0 the fraction -ipm_thr0 of the box width */
     double tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min;
+    int32_t dtype;        /* arithmetic type: MPCB_F64 (the reference computes in IEEE double); MPCB_F32 is rejected, see DESIGN.md */
     int32_t max_batch;    /* capacity of the persistent iterate (instances) */
     int32_t ws_batch;     /* instances of solver workspace resident at once (0 = auto) */
     int32_t device;       /* CUDA device ordinal, -1 = current */

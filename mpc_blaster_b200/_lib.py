@@ -21,7 +21,7 @@ class MpcbConfig(C.Structure):
                 ("lbx", C.c_double * 17), ("ubx", C.c_double * 17), ("lbu", C.c_double * 6), ("ubu", C.c_double * 6),
                 ("ipm_max_iter", C.c_int32), ("ipm_mu0", C.c_double), ("ipm_thr0", C.c_double),
                 ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double),
-                ("alpha_min", C.c_double), ("max_batch", C.c_int32), ("ws_batch", C.c_int32), ("device", C.c_int32)]
+                ("alpha_min", C.c_double), ("dtype", C.c_int32), ("max_batch", C.c_int32), ("ws_batch", C.c_int32), ("device", C.c_int32)]
 
 
 # every symbol include/mpcb.h declares

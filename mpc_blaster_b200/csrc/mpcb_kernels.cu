@@ -350,7 +350,7 @@ int mpcb_config_default(mpcb_config *cfg, int variant, int N)
     for (int i = 0; i < 6; i++) { cfg->R[i] = R[i]; cfg->lbu[i] = lbu[i]; cfg->ubu[i] = ubu[i]; }
     cfg->ipm_max_iter = 60; cfg->ipm_mu0 = 1e2; cfg->ipm_thr0 = -0.5;
     cfg->tol_stat = 1e-6; cfg->tol_eq = 1e-8; cfg->tol_ineq = 1e-8; cfg->tol_comp = 1e-8; cfg->alpha_min = 1e-8;
-    cfg->max_batch = 1024; cfg->ws_batch = 0; cfg->device = -1;
+    cfg->dtype = MPCB_F64; cfg->max_batch = 1024; cfg->ws_batch = 0; cfg->device = -1;
     return 0;
 }
 
@@ -359,6 +359,8 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     if (!cfg || !out) return fail(nullptr, "null argument");
     if (cfg->variant != 17 && cfg->variant != 12) return fail(nullptr, "variant must be 17 or 12");
     if (cfg->N < 2 || cfg->N > 4096) return fail(nullptr, "horizon out of range");
+    if (cfg->dtype != MPCB_F64)
+        return fail(nullptr, "only dtype = MPCB_F64 is implemented (an interior point with active state bounds is not viable in FP32, DESIGN.md)");
     if (cfg->max_batch < 1) return fail(nullptr, "max_batch must be >= 1");
     if (!(cfg->dt > 0) || !(cfg->mass > 0)) return fail(nullptr, "dt and mass must be positive");
     int ndev = 0;

@@ -70,9 +70,12 @@ class BlasterMPC:
     """
 
     def __init__(self, mass, J, l_x, l_y, N, Tf, c, Q, R, Q_t, blastThruster, statesBound, controlBound, *,
-                 batch: int = 1, variant: int = 17, device=None, ws_batch: int = 0, ipm_max_iter: int = 60,
+                 batch: int = 1, variant: int = 17, dtype=torch.float64, device=None, ws_batch: int = 0, ipm_max_iter: int = 60,
                  ipm_mu0: float = 1e2, ipm_thr0: float = -0.5, tol_stat: float = 1e-6, tol_eq: float = 1e-8,
                  tol_ineq: float = 1e-8, tol_comp: float = 1e-8, alpha_min: float = 1e-8):
+        if dtype != torch.float64:
+            raise NotImplementedError("only float64 is implemented: the reference computes in IEEE double and an interior "
+                                      "point with active state bounds is not viable in FP32 (DESIGN.md)")
         if not torch.cuda.is_available():
             raise MpcbError("BlasterMPC needs a CUDA device; this package has no CPU fallback")
         self.lib = _lib.load()
@@ -94,7 +97,7 @@ class BlasterMPC:
                 arr[i] = float(vals[i])
         cfg.ipm_max_iter, cfg.ipm_mu0, cfg.ipm_thr0 = ipm_max_iter, ipm_mu0, ipm_thr0
         cfg.tol_stat, cfg.tol_eq, cfg.tol_ineq, cfg.tol_comp, cfg.alpha_min = tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min
-        cfg.max_batch, cfg.ws_batch, cfg.device = self.batch, ws_batch, self.device.index
+        cfg.dtype, cfg.max_batch, cfg.ws_batch, cfg.device = 64, self.batch, ws_batch, self.device.index
         self.cfg = cfg
         self._h = C.c_void_p()
         if self.lib.mpcb_create(C.byref(cfg), C.byref(self._h)) != 0:

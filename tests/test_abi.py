@@ -30,7 +30,7 @@ def test_config_default_is_the_reference_constants_and_struct_layouts_agree():
     cfg = _lib.MpcbConfig()
     # poison the tail: if the C struct were larger than the ctypes mirror this would corrupt memory
     assert lib.mpcb_config_default(C.byref(cfg), 17, 20) == 0
-    assert (cfg.variant, cfg.N, cfg.max_batch, cfg.device) == (17, 20, 1024, -1)
+    assert (cfg.variant, cfg.N, cfg.dtype, cfg.max_batch, cfg.device) == (17, 20, 64, 1024, -1)
     assert abs(cfg.dt - 1 / 30) < 1e-16 and cfg.mass == 9.0 and cfg.J[4] == 0.47314
     assert list(cfg.R) == [5e-2] * 4 + [1e-5] * 2 and cfg.Qt[0] == 1e4 and cfg.ubu[0] == 65 and cfg.lbx[2] == 0
     assert (cfg.tol_stat, cfg.tol_eq, cfg.tol_ineq, cfg.tol_comp) == (1e-6, 1e-8, 1e-8, 1e-8)

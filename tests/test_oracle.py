@@ -210,3 +210,22 @@ def test_cost_matches_definition():
     ref = sum(0.5 * P.dt * (P.Q @ (X[k] - yref[:17]) ** 2 + P.R @ (U[k] - yref[17:]) ** 2) for k in range(5))
     ref += 0.5 * P.Qt @ (X[5] - yref[:17]) ** 2
     assert abs(bo.stage_cost(X, U, yref, P) - ref) < 1e-9 * abs(ref)
+
+
+def test_hover_closed_loop_golden_regression():
+    """Config 1: 200 closed-loop steps of the reference's scenario against the committed golden
+    trajectory (tests/golden/make_closed_loop_golden.py; our oracle's own output, i.e. a regression
+    pin).  The rigid-body states and thrusts must reproduce tightly; the swivel rates / gimbal
+    angles are only weakly determined and get a loose bound."""
+    g = np.load(os.path.join(G, "hover_closed_loop_golden.npz"))
+    P = bo.canonical_problem(20)
+    c = co.BatchRTI(P, 1, nthreads=1)
+    x = g["simX"][0][None].copy()
+    for s in range(60):
+        u0, X, U, st = c.solve(x, g["yref"])
+        assert st[0] == 0
+        assert np.abs(u0[0, :4] - g["simU"][s, :4]).max() < 1e-6
+        x = co.plant_step(P, x, u0)
+        assert np.abs(x[0, :12] - g["simX"][s + 1, :12]).max() < 1e-7
+        assert np.abs(x[0] - g["simX"][s + 1]).max() < 1e-3
+    assert abs(g["simX"][-1][2] - 3.5) < 0.02 and g["simX"][:, 8].max() < 1.0 + 1e-6  # reaches z = 3.5 riding vz <= 1
