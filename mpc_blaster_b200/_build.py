@@ -21,16 +21,17 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """`defines` / `out` build an experimental variant beside the product library (tools/ab.py)."""
+    if out is None and not force and not _stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-warn-spills",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out or LIB] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -42,8 +42,8 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build._stale():
+    path = os.environ.get("MPCB_LIB_OVERRIDE") or _build.LIB  # override: A/B builds of tools/ab.py only
+    if path == _build.LIB and _build._stale():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         if os.path.exists(nvcc):
             _build.build()

@@ -24,6 +24,8 @@
 
 namespace mpcb {
 
+constexpr double kMuDiverge = 1e2;  // infeasibility test: mu > kMuDiverge * mu0 (the CPU checkers apply the same test; no feasible instance of the test scenarios exceeds 3 * mu0)
+
 // Per-warp shared memory: two stage-record images (same offsets as the global record) plus
 // the data that is carried from one stage of a sweep to the next.
 // NSLOT = 2: the next stage's record is prefetched while the current one is processed (latency
@@ -385,6 +387,9 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
 
     for (it = 0; it < P.ipm_max_iter; it++) {
         if (!(est_g == est_g) || !(est_b == est_b) || !(mu == mu)) { status = ST_NAN; break; }
+        // diverging multipliers (mean complementarity 100 x its starting value) are the signature of
+        // an infeasible QP: stop instead of running to the iteration cap (same status as min-step)
+        if (mu > T(kMuDiverge) * mu0) { status = ST_MINSTEP; break; }
         if (est_g <= (T)P.tol_stat && est_b <= (T)P.tol_eq && est_d <= (T)P.tol_ineq && comp <= (T)P.tol_comp) {
             status = ST_OK;
             break;

@@ -106,8 +106,8 @@ class BlasterMPC:
 
     # ------------------------------------------------------------------ helpers
     @classmethod
-    def canonical(cls, N: int = 20, batch: int = 1, variant: int = 17, **kw):
-        """Constants of reference simulation_blaster.py:12-30 with dt = 1/30 s."""
+    def canonical(cls, N: int = 20, batch: int = 1, variant: int = 17, statesBound=None, controlBound=None, **kw):
+        """Constants of reference simulation_blaster.py:12-30 with dt = 1/30 s (bounds can be overridden)."""
         Q = np.diag([1e3] * 6 + [5.0] * 3 + [10.0] * 3 + [1e-2] * 2 + [1e3] * 3)
         R = np.diag([5e-2] * 4 + [1e-5] * 2)
         sb = np.array([[-1.5, -1.5, 0, -0.174532925, -0.174532925, -0.349066, -1.0, -1.0, -1.0, -0.0872665, -0.0872665,
@@ -116,6 +116,8 @@ class BlasterMPC:
                         1.22173, 0.523599, 1.5, 1.5, 2.5]])
         cb = np.array([[0, 0, 0, 0, -0.0872665, -0.0872665], [65, 65, 65, 65, 0.0872665, 0.0872665]], dtype=np.float64)
         J = np.diag([0.50781, 0.47314, 0.72975])
+        sb = sb if statesBound is None else np.asarray(statesBound, dtype=np.float64)
+        cb = cb if controlBound is None else np.asarray(controlBound, dtype=np.float64)
         return cls(9.0, J, 0.3434, 0.3475, N, N / 30.0, 0.03, Q, R, 10 * Q, 2.2 * 9.81, sb, cb, batch=batch,
                    variant=variant, **kw)
 

@@ -460,6 +460,9 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
         if not np.isfinite(res[0] + res[1] + mu):
             status = 1
             break
+        if mu > 1e2 * mu0:  # diverging multipliers = infeasible QP: stop early, same status as the min-step exit
+            status = 3
+            break
         if res[0] <= tol_stat and res[1] <= tol_eq and res[2] <= tol_ineq and comp <= tol_comp:
             status = 0
             break

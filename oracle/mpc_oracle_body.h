@@ -382,6 +382,8 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
         if (P->rg_mode == 2) { res_g = rg_est; res_b = rb_est; res_d = rd_est; }
         if (orc_debug()) fprintf(stderr, "it %d res_g %.3e res_b %.3e res_d %.3e comp %.3e mu %.3e\n", it, res_g, res_b, res_d, comp, mu);
         if (!(res_g == res_g) || !(res_b == res_b) || !(mu == mu)) { status = 1; break; }
+        /* diverging multipliers = infeasible QP: stop early, same status as the min-step exit */
+        if (mu > 1e2 * mu0) { status = 3; break; }
         if (res_g <= P->tol_stat && res_b <= P->tol_eq && res_d <= P->tol_ineq && comp <= P->tol_comp) { status = 0; break; }
         /* factorise with barrier diagonal */
         for (size_t i = 0; i < n; i++) w->Hd[i] = w->H0[i] + w->ll[i] / w->tl[i] + w->lu[i] / w->tu[i];
