@@ -61,6 +61,43 @@ def acados_json_args(path, N=None) -> dict:
                 ipm_max_iter=int(so["qp_solver_iter_max"]))
 
 
+def write_acados_json(path, *, N, Tf, Q, R, Q_t, blastThruster, statesBound, controlBound, ipm_max_iter=500, parameter_values=None):
+    """Write OCP data in the layout of the acados dump the reference commits
+    (src/scripts/acados_ocp_blasterModel.json, written at blastermodel.py:289): dims, LINEAR_LS
+    cost (W, W_e, Vx, Vu, Vx_e as blastermodel.py:244-257 builds them), box bounds with their index
+    sets (:261-270), default parameters (:280-282) and the solver options this solver implements
+    (:272-287).  ``acados_json_args`` / ``BlasterMPC.from_acados_json`` read it back."""
+    import json
+    nx, nu = 17, 6
+    Qd, Rd, Qtd = _diag(Q, nx, "Q"), _diag(R, nu, "R"), _diag(Q_t, nx, "Q_t")
+    sb, cb = np.asarray(statesBound, dtype=np.float64), np.asarray(controlBound, dtype=np.float64)
+    N, dt = int(N), float(Tf) / int(N)
+    W = np.diag(np.concatenate([Qd, Rd]))
+    Vx = np.vstack([np.eye(nx), np.zeros((nu, nx))])
+    Vu = np.vstack([np.zeros((nx, nu)), np.eye(nu)])
+    if parameter_values is None:
+        pv = np.zeros(25)
+        pv[24] = float(blastThruster)
+    else:
+        pv = np.asarray(parameter_values, dtype=np.float64).reshape(25)
+    d = {"dims": {"N": N, "nx": nx, "nu": nu, "np": 25, "ny": nx + nu, "ny_e": nx, "nbx": nx, "nbu": nu, "nbx_0": nx, "nbx_e": 0},
+         "cost": {"cost_type": "LINEAR_LS", "cost_type_0": "LINEAR_LS", "cost_type_e": "LINEAR_LS", "W": W.tolist(), "W_0": W.tolist(),
+                  "W_e": np.diag(Qtd).tolist(), "Vx": Vx.tolist(), "Vu": Vu.tolist(), "Vx_e": np.eye(nx).tolist(),
+                  "yref": [0.0] * (nx + nu), "yref_e": [0.0] * nx},
+         "constraints": {"constr_type": "BGH", "lbx": sb[0].tolist(), "ubx": sb[1].tolist(), "lbu": cb[0].tolist(), "ubu": cb[1].tolist(),
+                         "idxbx": list(range(nx)), "idxbu": list(range(nu)), "idxbxe_0": list(range(nx)), "idxbx_0": list(range(nx)),
+                         "lbx_0": [0.0] * nx, "ubx_0": [0.0] * nx},
+         "parameter_values": pv.tolist(),
+         "solver_options": {"tf": dt * N, "time_steps": [dt] * N, "nlp_solver_type": "SQP_RTI", "integrator_type": "ERK",
+                            "sim_method_num_stages": [4] * N, "sim_method_num_steps": [1] * N, "hessian_approx": "GAUSS_NEWTON",
+                            "qp_solver": "PARTIAL_CONDENSING_HPIPM", "qp_solver_cond_N": N, "qp_solver_iter_max": int(ipm_max_iter),
+                            "qp_solver_warm_start": 0, "globalization": "FIXED_STEP", "nlp_solver_step_length": 1.0,
+                            "levenberg_marquardt": 0.0}}
+    with open(path, "w") as f:
+        json.dump(d, f, indent=1)
+    return path
+
+
 class BlasterMPC:
     """B independent BLASTER controllers solved together on one GPU.
 
@@ -82,7 +119,7 @@ class BlasterMPC:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.nx, self.nu = (17, 6) if variant == 17 else (12, 4)
         self.ny, self.N, self.batch = self.nx + self.nu, int(N), int(batch)
-        self.blastThruster = blastThruster
+        self.blastThruster, self.variant = float(blastThruster), int(variant)
         cfg = MpcbConfig()
         cfg.variant, cfg.N, cfg.dt, cfg.mass = variant, int(N), float(Tf) / int(N), float(mass)
         cfg.J[:] = np.asarray(J, dtype=np.float64).reshape(9)
@@ -214,6 +251,17 @@ class BlasterMPC:
         J = np.diag([0.50781, 0.47314, 0.72975]) if J is None else J
         return cls(mass, J, l_x, l_y, a["N"], a["Tf"], c, a["Q"], a["R"], a["Q_t"], a["blastThruster"], a["statesBound"],
                    a["controlBound"], batch=batch, variant=variant, **kw)
+
+    def to_acados_json(self, path, parameter_values=None):
+        """Write this controller's OCP data in the acados dump layout (see ``write_acados_json``)."""
+        if self.variant != 17:
+            raise ValueError("the acados dump format describes the 17-state / 6-input OCP")
+        c, nx, nu = self.cfg, self.nx, self.nu
+        return write_acados_json(path, N=self.N, Tf=float(c.dt) * self.N, Q=[c.Q[i] for i in range(nx)], R=[c.R[i] for i in range(nu)],
+                                 Q_t=[c.Qt[i] for i in range(nx)], blastThruster=self.blastThruster,
+                                 statesBound=[[c.lbx[i] for i in range(nx)], [c.ubx[i] for i in range(nx)]],
+                                 controlBound=[[c.lbu[i] for i in range(nu)], [c.ubu[i] for i in range(nu)]],
+                                 ipm_max_iter=int(c.ipm_max_iter), parameter_values=parameter_values)
 
     def solve_host(self, x0, yref, p=None, want_traj: bool = False):
         """Same through ``mpcb_solve_host``: NumPy in, NumPy out, copies inside the call."""

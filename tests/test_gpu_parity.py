@@ -322,6 +322,13 @@ def test_from_acados_json_equals_canonical(cuda_device):
     b = _mpc(20, B)
     for s, t in zip(a.solve(x0, yref), b.solve(x0, yref)):
         assert torch.equal(s, t)
+    # write direction: dump the canonical controller, load the dump, same solver
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = BlasterMPC.from_acados_json(b.to_acados_json(os.path.join(d, "ocp.json")), batch=B, ipm_max_iter=60)
+    b.reset()
+    for s, t in zip(c.solve(x0, yref), b.solve(x0, yref)):
+        assert torch.equal(s, t)
 
 
 @pytest.mark.parametrize("variant,N,B", [(17, 2, 3), (12, 3, 5), (17, 80, 8), (17, 7, 33)])
