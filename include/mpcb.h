@@ -148,6 +148,27 @@ int64_t mpcb_kernel_launches(void);
  * normalised collective thrust from the cubic map of thrusterCumul(). quat[B,4], thrust[B]. */
 int mpcb_command_map(mpcb_handle *h, const double *x, const double *u0, double *quat, double *thrust, int B, void *stream);
 
+/* Jet point of contact (POC) and its Jacobians for B vehicle poses: the parameter generator that
+ * feeds p[0:24] of the OCP.  Replaces the reference's Jacobian_POC_Solver.solveJacobians()
+ * (src/scripts/Jacobian_POC_Solver.py:234-300, with setInitConditions :153-175, htm.py:7-36, the
+ * ERK jet integrator :59-99 and the Newton time-of-flight search :115-152), which the scripts run
+ * once on the CPU before the control loop (simulation_blaster.py:37-39).
+ *   poses: euler[B,3] (phi,theta,psi), motor[B,2] (alpha1,alpha2), position[B,3] -- or x17[B,17]
+ *          state vectors (then the three arrays may be NULL);
+ *   stream_velocity, drag: constructor arguments of the reference class (150, 1);
+ *   mode MPCB_POC_REFERENCE: the reference's algorithm step for step (RK4 x10, Newton with a
+ *          forward-difference slope to |z| <= 1e-3, forward differences eps = 1e-6);
+ *        MPCB_POC_ANALYTIC: closed-form flight, exact root, implicit-function Jacobians;
+ *   outputs (device pointers, any may be NULL): poc[B,3], J_mot[B,3,2], J_eul[B,3,3], J_pos[B,3,3]
+ *          row-major, p25[B,25] packed as simulation_blaster.py:67 does (column-major blocks, then
+ *          T_blast), t_flight[B], status[B] (0 ok, 1 NaN, 2 iteration cap).
+ * No handle: the call is stateless. */
+#define MPCB_POC_REFERENCE 0
+#define MPCB_POC_ANALYTIC 1
+int mpcb_poc_jacobians(const double *euler, const double *motor, const double *position, const double *x17, int B,
+                       double stream_velocity, double drag, int mode, double T_blast, double *poc, double *J_mot, double *J_eul,
+                       double *J_pos, double *p25, double *t_flight, int32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

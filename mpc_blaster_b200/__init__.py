@@ -5,7 +5,7 @@ hand-written CUDA for sm_100a behind the C ABI in include/mpcb.h.  No CPU fallba
 """
 from . import scenarios  # noqa: F401
 
-__all__ = ["BlasterMPC", "blasterModel", "scenarios"]
+__all__ = ["BlasterMPC", "blasterModel", "JacobianPOCSolver", "scenarios"]
 
 
 def __getattr__(name):
@@ -13,6 +13,9 @@ def __getattr__(name):
     if name == "BlasterMPC":
         from .solver import BlasterMPC
         return BlasterMPC
+    if name == "JacobianPOCSolver":
+        from .poc import JacobianPOCSolver
+        return JacobianPOCSolver
     if name == "blasterModel":
         from .acados_shim import blasterModel
         return blasterModel

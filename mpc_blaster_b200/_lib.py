@@ -28,7 +28,7 @@ class MpcbConfig(C.Structure):
 EXPORTS = ["mpcb_config_default", "mpcb_create", "mpcb_destroy", "mpcb_last_error", "mpcb_nx", "mpcb_nu", "mpcb_horizon",
            "mpcb_reset", "mpcb_solve", "mpcb_solve_host", "mpcb_plant_step", "mpcb_closed_loop", "mpcb_cost",
            "mpcb_get_iterate", "mpcb_set_iterate", "mpcb_debug_linearize", "mpcb_kernel_launches", "mpcb_command_map",
-           "mpcb_profile", "mpcb_last_kernel_ms", "mpcb_fp64_peak", "mpcb_solve_sqp", "mpcb_shift"]
+           "mpcb_profile", "mpcb_last_kernel_ms", "mpcb_fp64_peak", "mpcb_solve_sqp", "mpcb_shift", "mpcb_poc_jacobians"]
 
 _lib = None
 
@@ -71,6 +71,7 @@ def load() -> C.CDLL:
     lib.mpcb_set_iterate.argtypes = [vp, dp, dp, C.c_int, vp]
     lib.mpcb_debug_linearize.argtypes = [vp, dp, C.c_int, dp, dp, C.c_int, vp]
     lib.mpcb_command_map.argtypes = [vp, dp, dp, dp, dp, C.c_int, vp]
+    lib.mpcb_poc_jacobians.argtypes = [dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, dp, dp, dp, dp, dp, dp, ip, vp]
     lib.mpcb_kernel_launches.restype = C.c_int64
     lib.mpcb_profile.argtypes = [vp, C.c_int]
     lib.mpcb_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]

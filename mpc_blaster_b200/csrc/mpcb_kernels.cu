@@ -12,6 +12,7 @@
 #include "mpcb_common.cuh"
 #include "mpcb_linearize.cuh"
 #include "mpcb_qp.cuh"
+#include "mpcb_poc.cuh"
 
 using namespace mpcb;
 
@@ -201,6 +202,39 @@ __global__ void command_map_kernel(const double *__restrict__ x, const double *_
         const double avg = 2.3 * (0.25 * (u[0] + u[1] + u[2] + u[3])) / 9.81;
         thrust[i] = 0.0014 * avg * avg * avg - 0.0263 * avg * avg + 0.2464 * avg - 0.0286;
     }
+}
+
+// Jet point of contact and its Jacobians, one vehicle pose per thread (mpcb_poc.cuh;
+// reference Jacobian_POC_Solver.py:234-300).  x17 != nullptr: poses are read from state vectors
+// (position x[0:3], Euler angles x[3:6], nozzle angles x[12:14], blastermodel.py:171-190).
+__global__ void poc_kernel(const double *__restrict__ euler, const double *__restrict__ motor, const double *__restrict__ position,
+                           const double *__restrict__ x17, int B, double V, double drag, int mode, double T_blast,
+                           double *__restrict__ poc, double *__restrict__ J_mot, double *__restrict__ J_eul,
+                           double *__restrict__ J_pos, double *__restrict__ p25, double *__restrict__ t_flight, int32_t *__restrict__ status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double e[3], m[2], pos[3];
+    if (x17) {
+        const double *x = x17 + (size_t)i * 17;
+        for (int c = 0; c < 3; c++) { pos[c] = x[c]; e[c] = x[3 + c]; }
+        m[0] = x[12]; m[1] = x[13];
+    } else {
+        for (int c = 0; c < 3; c++) { pos[c] = position[(size_t)i * 3 + c]; e[c] = euler[(size_t)i * 3 + c]; }
+        m[0] = motor[(size_t)i * 2]; m[1] = motor[(size_t)i * 2 + 1];
+    }
+    PocOut o;
+    if (mode == POC_MODE_ANALYTIC) poc_analytic(e, m, pos, V, drag, o);
+    else poc_reference(e, m, pos, V, drag, o);
+    for (int r = 0; r < 3; r++) {
+        if (poc) poc[(size_t)i * 3 + r] = o.poc[r];
+        if (J_mot) for (int c = 0; c < 2; c++) J_mot[(size_t)i * 6 + r * 2 + c] = o.J[r][c];
+        if (J_eul) for (int c = 0; c < 3; c++) J_eul[(size_t)i * 9 + r * 3 + c] = o.J[r][2 + c];
+        if (J_pos) for (int c = 0; c < 3; c++) J_pos[(size_t)i * 9 + r * 3 + c] = o.J[r][5 + c];
+    }
+    if (p25) poc_pack_params(o, T_blast, p25 + (size_t)i * kNP);
+    if (t_flight) t_flight[i] = o.t_flight;
+    if (status) status[i] = o.status;
 }
 
 // FP64 FMA-pipe micro-benchmark: 8 independent DFMA chains per thread.
@@ -707,6 +741,24 @@ int mpcb_command_map(mpcb_handle *h, const double *x, const double *u0, double *
     command_map_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, u0, h->nx, h->nu, quat, thrust, B);
     g_launches += 1;
     CK(h, cudaGetLastError());
+    return 0;
+}
+
+int mpcb_poc_jacobians(const double *euler, const double *motor, const double *position, const double *x17, int B,
+                       double stream_velocity, double drag, int mode, double T_blast, double *poc, double *J_mot, double *J_eul,
+                       double *J_pos, double *p25, double *t_flight, int32_t *status, void *stream)
+{
+    if (B < 0) return fail(nullptr, "negative batch");
+    if (!x17 && (!euler || !motor || !position)) return fail(nullptr, "null argument: give euler/motor/position or x17");
+    if (mode != POC_MODE_REFERENCE && mode != POC_MODE_ANALYTIC) return fail(nullptr, "mode must be MPCB_POC_REFERENCE or MPCB_POC_ANALYTIC");
+    if (!(stream_velocity > 0) || !(drag > 0)) return fail(nullptr, "stream velocity and drag must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, "no CUDA device (this library has no CPU fallback)");
+    if (B == 0) return 0;
+    poc_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(euler, motor, position, x17, B, stream_velocity, drag, mode, T_blast, poc, J_mot,
+                                                               J_eul, J_pos, p25, t_flight, status);
+    g_launches += 1;
+    if (cudaGetLastError() != cudaSuccess) return fail(nullptr, "poc_kernel launch failed");
     return 0;
 }
 

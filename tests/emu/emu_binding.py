@@ -27,7 +27,7 @@ class Params(C.Structure):
 
 def build(force=False):
     srcs = [os.path.join(HERE, "emu_main.cpp"), os.path.join(HERE, "warp_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("mpcb_common.cuh", "mpcb_model.cuh", "mpcb_linearize.cuh", "mpcb_qp.cuh")]
+           [os.path.join(CSRC, f) for f in ("mpcb_common.cuh", "mpcb_model.cuh", "mpcb_linearize.cuh", "mpcb_qp.cuh", "mpcb_poc.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -93,3 +93,16 @@ def plant_step(P, x, u, p):
     lib().emu_plant_step(C.byref(o), _dp(np.ascontiguousarray(x, dtype=np.float64)), _dp(np.ascontiguousarray(u, dtype=np.float64)),
                          _dp(np.ascontiguousarray(p, dtype=np.float64)), _dp(xn))
     return xn
+
+
+def poc(euler, motor, position, V=150.0, drag=1.0, mode=0):
+    """-> (poc[3], J_mot[3,2], J_eul[3,3], J_pos[3,3], t_flight, status, p25)"""
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    e, m, p = (np.ascontiguousarray(a, dtype=np.float64) for a in (euler, motor, position))
+    out, p25 = np.zeros(29), np.zeros(25)
+    f = lib().emu_poc
+    f.argtypes = [C.POINTER(C.c_double)] * 3 + [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f.restype = None
+    f(dp(e), dp(m), dp(p), V, drag, mode, dp(out), dp(p25))
+    J = out[3:27].reshape(3, 8)
+    return out[:3].copy(), J[:, 0:2].copy(), J[:, 2:5].copy(), J[:, 5:8].copy(), out[27], int(out[28]), p25

@@ -11,6 +11,7 @@
 #include "mpcb_common.cuh"
 #include "mpcb_linearize.cuh"
 #include "mpcb_qp.cuh"
+#include "mpcb_poc.cuh"
 
 using namespace mpcb;
 
@@ -74,4 +75,18 @@ void emu_quat_mul(const double *a, const double *b, double *c) { quat_mul<double
 void emu_quat_inv(const double *q, double *r) { quat_inv_unit<double>(q, r); }
 void emu_quat_to_rot(const double *q, double *R) { quat_to_rot<double>(q, R); }
 void emu_euler_to_quat(double phi, double th, double psi, double *q) { euler_to_quat<double>(phi, th, psi, q); }
+}
+
+// mpcb_poc.cuh is plain per-thread code: run it directly.  out = [poc(3), J(3x8 row-major), t_flight, status]
+extern "C" void emu_poc(const double *e, const double *m, const double *pos, double V, double drag, int mode, double *out, double *p25)
+{
+    PocOut o;
+    if (mode == POC_MODE_ANALYTIC) poc_analytic(e, m, pos, V, drag, o);
+    else poc_reference(e, m, pos, V, drag, o);
+    for (int i = 0; i < 3; i++) out[i] = o.poc[i];
+    for (int i = 0; i < 3; i++)
+        for (int c = 0; c < 8; c++) out[3 + i * 8 + c] = o.J[i][c];
+    out[27] = o.t_flight;
+    out[28] = o.status;
+    if (p25) poc_pack_params(o, 21.582, p25);
 }

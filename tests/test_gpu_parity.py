@@ -415,3 +415,51 @@ def test_hover_closed_loop_against_golden_trajectory(cuda_device):
     assert vz_max < 1.0 + 1e-3
     assert np.abs(x[0, :3].cpu().numpy() - g["simX"][-1][:3]).max() < 0.05
     assert abs(float(x[0, 2]) - 3.5) < 0.05
+
+
+def test_poc_jacobian_generator(cuda_device):
+    """mpcb_poc_jacobians against the golden values produced by the reference's own
+    Jacobian_POC_Solver.py (tests/golden/make_poc_golden.py), the oracle, and the reference's call
+    sequence simulation_blaster.py:37-39 through the mirror class."""
+    import os
+    from mpc_blaster_b200.poc import JacobianPOCSolver
+    from oracle import poc_oracle as po
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "poc_golden.npz"))
+    s = JacobianPOCSolver(150, 1, 0.000015)
+    o = s.solve_batch(g["euler"], g["motor"], g["position"], T_blast=2.2 * 9.81)
+    assert int(o["status"].abs().sum()) == 0
+    assert np.abs(o["poc"].cpu().numpy() - g["poc"]).max() < 1e-11
+    assert np.abs(o["t_flight"].cpu().numpy() - g["t_flight"]).max() < 1e-13
+    for k in ("J_mot", "J_eul", "J_pos"):  # forward differences with eps = 1e-6 amplify rounding by 1e6
+        assert np.abs(o[k].cpu().numpy() - g[k]).max() < 5e-6, k
+    p = o["p"].cpu().numpy()
+    for i in range(p.shape[0]):  # packing of simulation_blaster.py:67
+        ref = np.concatenate([o[k][i].cpu().numpy().reshape(-1, order="F") for k in ("J_mot", "J_eul", "J_pos")] + [[2.2 * 9.81]])
+        assert np.array_equal(p[i], ref)
+    # the reference's own three lines
+    s.initialise()
+    J_mot, J_eul, J_pos = s.getJacobians()
+    assert np.abs(J_mot - g["init_J_mot"]).max() < 5e-6 and np.abs(J_eul - g["init_J_eul"]).max() < 5e-6
+    assert np.abs(J_pos - g["init_J_pos"]).max() < 5e-6
+    # exact mode against the oracle's exact counterpart
+    a = JacobianPOCSolver(150, 1, 0.000015, mode="analytic").solve_batch(g["euler"], g["motor"], g["position"])
+    for i in range(g["euler"].shape[0]):
+        ref = po.analytic_jacobians(g["euler"][i], g["motor"][i], g["position"][i])
+        assert np.abs(a["poc"][i].cpu().numpy() - ref[0]).max() < 1e-12
+        for k, r in zip(("J_mot", "J_eul", "J_pos"), ref[1:4]):
+            assert np.abs(a[k][i].cpu().numpy() - r).max() < 1e-6
+    # from state vectors, per vehicle, and fed to the solver as per-instance parameters
+    B = 4096
+    x0, yref = sc.random_setpoints(B, seed=9)
+    pB = JacobianPOCSolver(150, 1, 0.000015, mode="analytic").params_from_states(x0, 2.2 * 9.81)
+    chk = JacobianPOCSolver(150, 1, 0.000015, mode="analytic").solve_batch(x0[:, 3:6], x0[:, 12:14], x0[:, 0:3], T_blast=2.2 * 9.81)["p"]
+    assert torch.equal(pB, chk) and bool(torch.isfinite(pB).all())
+    mpc = _mpc(10, 64)
+    mpc.reset(x0[:64], sc.hover_trim())
+    u0, X, U, st = mpc.solve(x0[:64], yref[:64], p=pB[:64])
+    orc = co.BatchRTI(bo.canonical_problem(10), 64)
+    orc.reset(x0[:64], sc.hover_trim())
+    uo, Xo, Uo, sto = orc.solve(x0[:64], yref[:64], pB[:64].cpu().numpy())
+    ok = sto == 0
+    assert (st.cpu().numpy() == sto).all() and ok.mean() > 0.9
+    assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL

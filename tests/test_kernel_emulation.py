@@ -84,3 +84,29 @@ def test_quaternion_helpers_match_reference_mathutils():
     lib.emu_euler_to_quat(0.13, -0.07, 0.31, dp(q))
     lib.emu_quat_to_rot(dp(q), dp(R))
     assert np.abs(R.reshape(3, 3) - bo._rot(0.13, -0.07, 0.31)).max() < 1e-15
+
+
+def test_emulated_poc_generator_matches_oracle_and_reference_golden():
+    """mpcb_poc.cuh compiled for the host against (a) the golden values produced by the reference's
+    own Jacobian_POC_Solver.py / htm.py (tests/golden/make_poc_golden.py) and (b) the oracle.
+    Forward differences with eps = 1e-6 amplify rounding differences by 1e6, hence 5e-6 on the
+    Jacobians; the analytic mode is compared with the oracle's exact counterpart."""
+    from oracle import poc_oracle as po
+    g = np.load(os.path.join(G, "poc_golden.npz"))
+    for i in range(g["euler"].shape[0]):
+        e, m, p = g["euler"][i], g["motor"][i], g["position"][i]
+        poc, Jm, Je, Jp, tf, st, p25 = eb.poc(e, m, p, mode=0)
+        assert st == 0
+        assert np.abs(poc - g["poc"][i]).max() < 1e-11 and abs(tf - g["t_flight"][i]) < 1e-13
+        assert np.abs(Jm - g["J_mot"][i]).max() < 5e-6 and np.abs(Je - g["J_eul"][i]).max() < 5e-6
+        assert np.abs(Jp - g["J_pos"][i]).max() < 5e-6
+        # packing of simulation_blaster.py:67
+        ref = np.concatenate([Jm.reshape(-1, order="F"), Je.reshape(-1, order="F"), Jp.reshape(-1, order="F"), [21.582]])
+        assert np.array_equal(p25, ref)
+        poc_a, Jm_a, Je_a, Jp_a, tf_a, st_a, _ = eb.poc(e, m, p, mode=1)
+        o = po.analytic_jacobians(e, m, p)
+        assert st_a == 0 and abs(poc_a[2]) < 1e-12
+        assert np.abs(poc_a - o[0]).max() < 1e-12 and abs(tf_a - o[4]) < 1e-14
+        assert np.abs(Jm_a - o[1]).max() < 1e-6 and np.abs(Je_a - o[2]).max() < 1e-6 and np.abs(Jp_a - o[3]).max() < 1e-6
+        # the exact Jacobians differ from the reference's by what its |z| <= 1e-3 root tolerance leaves
+        assert np.abs(Jm_a - Jm).max() < 2e-3 and np.abs(Je_a - Je).max() < 2e-3 and np.abs(Jp_a - Jp).max() < 2e-3

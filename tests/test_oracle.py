@@ -229,3 +229,29 @@ def test_hover_closed_loop_golden_regression():
         assert np.abs(x[0, :12] - g["simX"][s + 1, :12]).max() < 1e-7
         assert np.abs(x[0] - g["simX"][s + 1]).max() < 1e-3
     assert abs(g["simX"][-1][2] - 3.5) < 0.02 and g["simX"][:, 8].max() < 1.0 + 1e-6  # reaches z = 3.5 riding vz <= 1
+
+
+def test_poc_oracle_reproduces_the_reference_jacobian_poc_solver():
+    """oracle/poc_oracle.py against tests/golden/poc_golden.npz, i.e. against outputs of the
+    reference's own Jacobian_POC_Solver.py and htm.py (run by tests/golden/make_poc_golden.py):
+    homogeneous transforms, jet initial state, time of flight, POC and the three Jacobians for 12
+    poses, and the Jacobians of the reference's initialise() call (simulation_blaster.py:37-39)."""
+    from oracle import poc_oracle as po
+    g = np.load(os.path.join(G, "poc_golden.npz"))
+    V, c = float(g["stream_velocity"]), float(g["M_c"])
+    for i in range(g["euler"].shape[0]):
+        e, m, p = g["euler"][i], g["motor"][i], g["position"][i]
+        assert np.abs(po.T_b_s2(*m) - g["T_b_s2"][i]).max() < 1e-15
+        assert np.abs(po.T_w_b(*e, p) - g["T_w_b"][i]).max() < 1e-15
+        x0 = po.init_conditions(e, m, p, V)
+        assert np.abs(x0 - g["x_init"][i]).max() < 1e-12
+        assert abs(po.time_of_flight(x0, c) - g["t_flight"][i]) < 1e-14
+        poc, Jm, Je, Jp = po.solve_jacobians(e, m, p, V, c)
+        assert np.abs(poc - g["poc"][i]).max() < 1e-11
+        assert np.abs(Jm - g["J_mot"][i]).max() < 5e-6 and np.abs(Je - g["J_eul"][i]).max() < 5e-6
+        assert np.abs(Jp - g["J_pos"][i]).max() < 5e-6
+    _, Jm, Je, Jp = po.solve_jacobians([0, 0, 0], [0, 0], [0, 0, 4], V, c)
+    assert np.abs(Jm - g["init_J_mot"]).max() < 5e-6 and np.abs(Je - g["init_J_eul"]).max() < 5e-6 and np.abs(Jp - g["init_J_pos"]).max() < 5e-6
+    # the ndarray call pattern of the reference accumulates the position perturbations (documented, not a target)
+    acc = np.cumsum(g["J_pos"][0], axis=1)
+    assert np.abs(acc - g["J_pos_ndarray_call"]).max() < 1e-3
