@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmpcb.so")
 SOURCES = ["mpcb_kernels.cu"]
-HEADERS = ["mpcb_common.cuh", "mpcb_model.cuh", "mpcb_linearize.cuh", "mpcb_qp.cuh", "mpcb_poc.cuh"]
+HEADERS = ["mpcb_common.cuh", "mpcb_model.cuh", "mpcb_linearize.cuh", "mpcb_qp.cuh", "mpcb_qp8.cuh", "mpcb_poc.cuh"]
 
 
 def _stale() -> bool:

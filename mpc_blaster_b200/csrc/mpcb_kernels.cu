@@ -12,6 +12,7 @@
 #include "mpcb_common.cuh"
 #include "mpcb_linearize.cuh"
 #include "mpcb_qp.cuh"
+#include "mpcb_qp8.cuh"
 #include "mpcb_poc.cuh"
 
 using namespace mpcb;
@@ -82,6 +83,37 @@ __global__ void __launch_bounds__(32 * WPB, MINB) qp_kernel(const __grid_constan
     }
     __syncwarp();
     if (u0 && lane < NU) u0[(size_t)inst * NU + lane] = Ui[lane];
+}
+
+// K2': four instances per warp, eight lanes each (mpcb_qp8.cuh): the throughput variant for chunks of many waves.
+template <int NX, int NU>
+__global__ void __launch_bounds__(32) qp8_kernel(const __grid_constant__ Params P, double *__restrict__ X, double *__restrict__ U,
+                                                 const double *__restrict__ x0, const double *__restrict__ yref, int yref_mode,
+                                                 double *__restrict__ ws, double *__restrict__ u0, int32_t *__restrict__ status,
+                                                 int32_t *__restrict__ iters, int inst0, int B)
+{
+    using L = Layout<NX, NU>;
+    __shared__ Qp8Smem<NX, NU> sm;
+    const int N = P.N;
+    const int lane = threadIdx.x & 31, s = lane & (kLPI - 1);
+    int li = blockIdx.x * kGPW + (lane >> 3);
+    const bool act = li < B;
+    if (!act) li = B - 1;  // valid addresses; an inactive group neither reads nor writes through them
+    const int inst = inst0 + li;
+    double *Xi = X + (size_t)inst * (N + 1) * NX;
+    double *Ui = U + (size_t)inst * N * NU;
+    const double *yr = yref;
+    if (yref_mode == MPCB_PER_INSTANCE) yr = yref + (size_t)inst * (NX + NU);
+    if (yref_mode == MPCB_PER_STAGE) yr = yref + (size_t)inst * (N + 1) * (NX + NU);
+    int it = 0;
+    const int st = qp8_solve_warp<NX, NU>(P, sm, ws + (size_t)li * L::instance_stride(N), Xi, Ui, x0 + (size_t)inst * NX, yr,
+                                          yref_mode == MPCB_PER_STAGE, act, &it);
+    if (act && s == 0) {
+        if (status) status[inst] = st;
+        if (iters) iters[inst] = it;
+    }
+    __syncwarp();
+    if (act && u0 && s < NU) u0[(size_t)inst * NU + s] = Ui[s];
 }
 
 template <int NX, int NU>
@@ -268,6 +300,7 @@ struct mpcb_handle {
     size_t d_stage_bytes = 0;
     cudaStream_t own_stream = nullptr;
     int throughput_batch = 1 << 30;  // chunks at least this large use the high-occupancy QP kernel variant
+    int qp8_batch = 1 << 30;         // chunks at least this large use the four-instances-per-warp kernel
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around K1 and K2 of the last solve (profiling)
     bool profile = false;
     std::string err;
@@ -340,7 +373,9 @@ int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, in
         if (prof) cudaEventRecord(h->ev[0], s);
         linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
         if (prof) cudaEventRecord(h->ev[1], s);
-        if (nb >= h->throughput_batch)
+        if (nb >= h->qp8_batch)
+            qp8_kernel<NX, NU><<<(nb + kGPW - 1) / kGPW, 32, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb);
+        else if (nb >= h->throughput_batch)
             qp_kernel<NX, NU, kWPB, 1, 12><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
                                                                                              h->ws, u0, status, iters, i0, nb);
         else
@@ -430,6 +465,11 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         // more than ~2 waves of the latency variant (9 warps x 148 SMs): switch to the throughput variant
         const char *tb = getenv("MPCB_THROUGHPUT_BATCH");
         h->throughput_batch = tb ? atoi(tb) : 4096;
+        // four-instances-per-warp kernel: measured faster from ~4,096 instances on for QUAD12 (+11 % there, +17 % at
+        // 16,384, +32 % at 65,536); for BLASTER17 its 36 KB of shared memory per warp leave 6 warps per SM and it
+        // stays ~7 % behind the one-instance kernel, so it is opt-in there (MPCB_QP8_BATCH=<chunk size>).
+        const char *q8 = getenv("MPCB_QP8_BATCH");
+        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 12 ? 4096 : (1 << 30));
     }
     const size_t B = (size_t)h->max_batch;
     const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;

@@ -27,7 +27,7 @@ class Params(C.Structure):
 
 def build(force=False):
     srcs = [os.path.join(HERE, "emu_main.cpp"), os.path.join(HERE, "warp_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("mpcb_common.cuh", "mpcb_model.cuh", "mpcb_linearize.cuh", "mpcb_qp.cuh", "mpcb_poc.cuh")]
+           [os.path.join(CSRC, f) for f in ("mpcb_common.cuh", "mpcb_model.cuh", "mpcb_linearize.cuh", "mpcb_qp.cuh", "mpcb_qp8.cuh", "mpcb_poc.cuh")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -106,3 +106,18 @@ def poc(euler, motor, position, V=150.0, drag=1.0, mode=0):
     f(dp(e), dp(m), dp(p), V, drag, mode, dp(out), dp(p25))
     J = out[3:27].reshape(3, 8)
     return out[:3].copy(), J[:, 0:2].copy(), J[:, 2:5].copy(), J[:, 5:8].copy(), out[27], int(out[28]), p25
+
+
+def rti_solve4(P, X, U, x0, yref, p, **opts):
+    """One emulated RTI iteration of up to four instances in one warp (mpcb_qp8.cuh).
+    X[nb,N+1,nx], U[nb,N,nu] are updated in place; returns (status[nb], iters[nb])."""
+    o = make_params(P, **opts)
+    nb = X.shape[0]
+    assert 1 <= nb <= 4 and X.flags.c_contiguous and U.flags.c_contiguous
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(nb, P.nx)
+    yref = np.ascontiguousarray(yref, dtype=np.float64).reshape(nb, P.nx + P.nu)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    st, it = np.zeros(nb, dtype=np.int32), np.zeros(nb, dtype=np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    lib().emu_rti_solve4(C.byref(o), nb, _dp(X), _dp(U), _dp(x0), _dp(yref), _dp(p), ip(st), ip(it))
+    return st, it

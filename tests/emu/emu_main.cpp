@@ -11,6 +11,7 @@
 #include "mpcb_common.cuh"
 #include "mpcb_linearize.cuh"
 #include "mpcb_qp.cuh"
+#include "mpcb_qp8.cuh"
 #include "mpcb_poc.cuh"
 
 using namespace mpcb;
@@ -89,4 +90,41 @@ extern "C" void emu_poc(const double *e, const double *m, const double *pos, dou
     out[27] = o.t_flight;
     out[28] = o.status;
     if (p25) poc_pack_params(o, 21.582, p25);
+}
+
+// Four instances per warp (mpcb_qp8.cuh).  X[nb][(N+1)*NX], U[nb][N*NU], x0[nb][NX], yref[nb][NY] (shared over stages), p[25];
+// nb <= 4 instances: groups beyond nb are inactive.
+template <int NX, int NU>
+static void rti_four(const Params &P, int nb, double *X, double *U, const double *x0, const double *yref, const double *p, int *status,
+                     int *iters)
+{
+    using L = Layout<NX, NU>;
+    const int N = P.N;
+    const size_t stride = L::instance_stride(N);
+    std::vector<double> ws(stride * nb, 0.0);
+    for (int b = 0; b < nb; b++)
+        for (int k = 0; k < N; k++) {
+            double *Xb = X + (size_t)b * (N + 1) * NX, *Ub = U + (size_t)b * N * NU;
+            emu::run_warp([&]() {
+                linearize_warp<NX, NU, double>(P, Xb + (size_t)k * NX, Ub + (size_t)k * NU, Xb + (size_t)(k + 1) * NX, p,
+                                               ws.data() + b * stride + (size_t)k * L::STAGE);
+            });
+        }
+    static Qp8Smem<NX, NU> sm;
+    memset(&sm, 0, sizeof(sm));
+    emu::run_warp([&]() {
+        int g = emu::lane() >> 3;
+        const bool act = g < nb;
+        if (!act) g = nb - 1;
+        int my_it = 0;
+        int st = qp8_solve_warp<NX, NU>(P, sm, ws.data() + g * stride, X + (size_t)g * (N + 1) * NX, U + (size_t)g * N * NU,
+                                        x0 + (size_t)g * NX, yref + (size_t)g * (NX + NU), 0, act, &my_it);
+        if (act && (emu::lane() & 7) == 0) { status[g] = st; iters[g] = my_it; }
+    });
+}
+extern "C" void emu_rti_solve4(const Params *P, int nb, double *X, double *U, const double *x0, const double *yref, const double *p,
+                               int *status, int *iters)
+{
+    if (P->variant == 17) rti_four<17, 6>(*P, nb, X, U, x0, yref, p, status, iters);
+    else rti_four<12, 4>(*P, nb, X, U, x0, yref, p, status, iters);
 }

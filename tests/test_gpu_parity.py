@@ -463,3 +463,34 @@ def test_poc_jacobian_generator(cuda_device):
     ok = sto == 0
     assert (st.cpu().numpy() == sto).all() and ok.mean() > 0.9
     assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+
+
+@pytest.mark.parametrize("variant,N,B", [(12, 20, 1024), (17, 20, 515), (12, 40, 130), (17, 7, 5)])
+def test_four_instances_per_warp_kernel_matches_c_oracle(cuda_device, variant, N, B, monkeypatch):
+    """The throughput variant of the QP kernel (mpcb_qp8.cuh: four instances per warp), forced for
+    every chunk size, against the C oracle on identical inputs -- including batch sizes that leave
+    the last warp partly empty -- and against the one-instance-per-warp kernel."""
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.random_setpoints(B, seed=77, nx=P.nx, nu=P.nu)
+    trim = sc.hover_trim(P.nu)
+    monkeypatch.setenv("MPCB_QP8_BATCH", "1")
+    mpc8 = _mpc(N, B, variant)
+    monkeypatch.setenv("MPCB_QP8_BATCH", str(1 << 30))
+    mpc1 = _mpc(N, B, variant)
+    orc = co.BatchRTI(P, B)
+    for m in (mpc8, mpc1, orc):
+        m.reset(x0, trim)
+    x = x0
+    for step in range(2):
+        u8, X8, U8, st8 = mpc8.solve(x, yref)
+        u1, X1, U1, st1 = mpc1.solve(x, yref)
+        uo, Xo, Uo, sto = orc.solve(x, yref)
+        st8 = st8.cpu().numpy()
+        assert (st8 == sto).all() and (st1.cpu().numpy() == sto).all()
+        ok = sto == 0
+        assert ok.mean() > 0.95
+        assert (mpc8.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
+        assert np.abs(U8.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X8.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+        assert np.abs(u8.cpu().numpy()[ok] - uo[ok]).max() < TOL
+        assert np.abs((U8 - U1).cpu().numpy()[ok]).max() < TOL and np.abs((X8 - X1).cpu().numpy()[ok]).max() < TOL
+        x = co.plant_step(P, x, uo)

@@ -110,3 +110,24 @@ def test_emulated_poc_generator_matches_oracle_and_reference_golden():
         assert np.abs(Jm_a - o[1]).max() < 1e-6 and np.abs(Je_a - o[2]).max() < 1e-6 and np.abs(Jp_a - o[3]).max() < 1e-6
         # the exact Jacobians differ from the reference's by what its |z| <= 1e-3 root tolerance leaves
         assert np.abs(Jm_a - Jm).max() < 2e-3 and np.abs(Je_a - Je).max() < 2e-3 and np.abs(Jp_a - Jp).max() < 2e-3
+
+
+@pytest.mark.parametrize("variant,N,nb", [(17, 10, 4), (12, 10, 4), (17, 6, 3), (12, 5, 1)])
+def test_emulated_four_instances_per_warp_kernel_matches_oracle(variant, N, nb):
+    """mpcb_qp8.cuh (four instances per warp, eight lanes each) compiled for the host: full and
+    partly filled warps, two RTI steps (the four instances then differ in their IPM iteration
+    counts, so groups finish at different times), against the C oracle."""
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.random_setpoints(nb, seed=31, nx=P.nx, nu=P.nu)
+    p = bo.default_params()
+    X = np.repeat(x0[:, None, :], N + 1, axis=1).copy()
+    U = np.tile(sc.hover_trim(P.nu), (nb, N, 1)).copy()
+    c = co.BatchRTI(P, nb, nthreads=1)
+    c.reset(x0, sc.hover_trim(P.nu))
+    x = x0.copy()
+    for step in range(2):
+        st, it = eb.rti_solve4(P, X, U, x, yref, p)
+        u0, Xc, Uc, stc = c.solve(x, yref, p)
+        assert (st == stc).all() and (st == 0).all() and (it == c.iters).all()
+        assert np.abs(Xc - X).max() < 1e-8 and np.abs(Uc - U).max() < 1e-7
+        x = co.plant_step(P, x, u0)
