@@ -29,7 +29,14 @@ struct Qp8Group {
     double vz[L::NZP];               // a stage vector every lane of the group reads (z_k or dz_k)
     double hd[L::NZP], ds[L::NZP];   // Hd_k and sqrt(Hd_k) of every row (pivot loop)
     double cPi[L::NXP], cZx[L::NXP], cPv[L::NXP], cDx[L::NXP], sT1[L::NXP], sT2[L::NXP], sRb[L::NXP];
+    // Pad so that consecutive groups are 32 bytes (mod 128) apart: the four groups of a warp then hit
+    // distinct banks when each broadcasts one word to its lanes, and a 64-byte run per group splits into
+    // the minimal two wavefronts.  (QUAD12's unpadded group is a multiple of 128 bytes: every broadcast
+    // was a 4-way bank conflict, 43 % of all shared-memory wavefronts in ncu.)
+    static constexpr int kBody = L::O_Z + L::LXX + 2 * L::NXP + 3 * L::NZP + 7 * L::NXP;
+    double pad[(4 - kBody % 16 + 16) % 16 == 0 ? 16 : (4 - kBody % 16 + 16) % 16];
 };
+static_assert(sizeof(Qp8Group<17, 6>) % 128 == 32 && sizeof(Qp8Group<12, 4>) % 128 == 32, "group stride must be 32 mod 128 bytes");
 template <int NX, int NU>
 struct Qp8Smem {
     Qp8Group<NX, NU> g[kGPW];
