@@ -149,7 +149,7 @@ def run_reference(args):
                              "mean_ipm_iters": iters, "converged_frac": ok},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------- GPU arm
@@ -319,12 +319,26 @@ def run_gpu(args):
             "solver": {"mean_ipm_iters": iters_mean, "converged_frac": ok_frac,
                        "p50_ms": float(np.percentile(step_ms, 50)), "p99_ms": float(np.percentile(step_ms, 99))},
             "cpu_baseline": cpu, "quad12": quad12}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Native libraries print to fd 1 (NCCL's version banner under torchrun, for one): keep the
+    # original stdout for the JSON line alone and send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

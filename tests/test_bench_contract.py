@@ -11,8 +11,8 @@ def test_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr
-    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 1
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1, out.stdout  # stdout carries the JSON line and nothing else
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "solves/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
