@@ -494,3 +494,23 @@ def test_four_instances_per_warp_kernel_matches_c_oracle(cuda_device, variant, N
         assert np.abs(u8.cpu().numpy()[ok] - uo[ok]).max() < TOL
         assert np.abs((U8 - U1).cpu().numpy()[ok]).max() < TOL and np.abs((X8 - X1).cpu().numpy()[ok]).max() < TOL
         x = co.plant_step(P, x, uo)
+
+
+def test_quad12_default_scheduler_mixes_both_qp_kernels(cuda_device):
+    """QUAD12 with the default scheduler settings: chunks of >= 4,096 instances go to the
+    four-instances-per-warp kernel, the remainder chunk to the one-instance kernel; a batch size that
+    is no multiple of four leaves the last warp partly empty.  Every instance against the C oracle."""
+    B, N = 9003, 8
+    P = bo.canonical_problem(N, 12)
+    x0, yref = sc.random_setpoints(B, seed=21, nx=12, nu=4)
+    mpc = _mpc(N, B, 12, ws_batch=4099)   # chunks of 4099 (qp8, last warp 3/4 full), 4099, 805 (one-instance kernel)
+    orc = co.BatchRTI(P, B)
+    mpc.reset(x0, sc.hover_trim(4))
+    orc.reset(x0, sc.hover_trim(4))
+    u0, X, U, st = mpc.solve(x0, yref)
+    uo, Xo, Uo, sto = orc.solve(x0, yref)
+    assert (st.cpu().numpy() == sto).all()
+    ok = sto == 0
+    assert ok.mean() > 0.97 and (mpc.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
+    assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+    assert np.abs(u0.cpu().numpy()[ok] - uo[ok]).max() < TOL
