@@ -86,34 +86,20 @@ __global__ void __launch_bounds__(32 * WPB, MINB) qp_kernel(const __grid_constan
 }
 
 // K2': four instances per warp, eight lanes each (mpcb_qp8.cuh): the throughput variant for chunks of many waves.
+// Persistent: the grid is one wave of resident warps, whose groups draw the chunk's instances from `next`.
 template <int NX, int NU>
 __global__ void __launch_bounds__(32) qp8_kernel(const __grid_constant__ Params P, double *__restrict__ X, double *__restrict__ U,
                                                  const double *__restrict__ x0, const double *__restrict__ yref, int yref_mode,
                                                  double *__restrict__ ws, double *__restrict__ u0, int32_t *__restrict__ status,
-                                                 int32_t *__restrict__ iters, int inst0, int B)
+                                                 int32_t *__restrict__ iters, int inst0, int B, unsigned *__restrict__ next)
 {
-    using L = Layout<NX, NU>;
     __shared__ Qp8Smem<NX, NU> sm;
-    const int N = P.N;
-    const int lane = threadIdx.x & 31, s = lane & (kLPI - 1);
-    int li = blockIdx.x * kGPW + (lane >> 3);
-    const bool act = li < B;
-    if (!act) li = B - 1;  // valid addresses; an inactive group neither reads nor writes through them
-    const int inst = inst0 + li;
-    double *Xi = X + (size_t)inst * (N + 1) * NX;
-    double *Ui = U + (size_t)inst * N * NU;
-    const double *yr = yref;
-    if (yref_mode == MPCB_PER_INSTANCE) yr = yref + (size_t)inst * (NX + NU);
-    if (yref_mode == MPCB_PER_STAGE) yr = yref + (size_t)inst * (N + 1) * (NX + NU);
-    int it = 0;
-    const int st = qp8_solve_warp<NX, NU>(P, sm, ws + (size_t)li * L::instance_stride(N), Xi, Ui, x0 + (size_t)inst * NX, yr,
-                                          yref_mode == MPCB_PER_STAGE, act, &it);
-    if (act && s == 0) {
-        if (status) status[inst] = st;
-        if (iters) iters[inst] = it;
-    }
-    __syncwarp();
-    if (act && u0 && s < NU) u0[(size_t)inst * NU + s] = Ui[s];
+    Qp8Batch job;
+    job.X = X; job.U = U; job.x0 = x0; job.yref = yref;
+    job.yref_stride = yref_mode == MPCB_PER_INSTANCE ? (size_t)(NX + NU) : yref_mode == MPCB_PER_STAGE ? (size_t)(P.N + 1) * (NX + NU) : 0;
+    job.yps = yref_mode == MPCB_PER_STAGE;
+    job.ws = ws; job.u0 = u0; job.status = status; job.iters = iters; job.inst0 = inst0; job.B = B; job.next = next;
+    qp8_solve_queue<NX, NU>(P, sm, job);
 }
 
 template <int NX, int NU>
@@ -301,6 +287,8 @@ struct mpcb_handle {
     cudaStream_t own_stream = nullptr;
     int throughput_batch = 1 << 30;  // chunks at least this large use the high-occupancy QP kernel variant
     int qp8_batch = 1 << 30;         // chunks at least this large use the four-instances-per-warp kernel
+    int qp8_resident = 1;            // warps of that kernel one wave holds (SMs x resident CTAs per SM)
+    unsigned *qp8_next = nullptr;    // its work counter
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around K1 and K2 of the last solve (profiling)
     bool profile = false;
     std::string err;
@@ -373,8 +361,13 @@ int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, in
         if (prof) cudaEventRecord(h->ev[0], s);
         linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
         if (prof) cudaEventRecord(h->ev[1], s);
-        if (nb >= h->qp8_batch)
-            qp8_kernel<NX, NU><<<(nb + kGPW - 1) / kGPW, 32, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb);
+        if (nb >= h->qp8_batch) {
+            // one wave of resident warps; their groups draw the chunk's instances from the work counter
+            const int want = (nb + kGPW - 1) / kGPW;
+            const int grid = want < h->qp8_resident ? want : h->qp8_resident;
+            CK(h, cudaMemsetAsync(h->qp8_next, 0, sizeof(unsigned), s));
+            qp8_kernel<NX, NU><<<grid, 32, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb, h->qp8_next);
+        }
         else if (nb >= h->throughput_batch)
             qp_kernel<NX, NU, kWPB, 1, 12><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
                                                                                              h->ws, u0, status, iters, i0, nb);
@@ -486,7 +479,17 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     ALLOC(h->iters_scratch, B * sizeof(int32_t));
     ALLOC(h->xn_scratch, B * h->nx * sizeof(double));
     ALLOC(h->u0_scratch, B * h->nu * sizeof(double));
+    ALLOC(h->qp8_next, sizeof(unsigned));
 #undef ALLOC
+    {
+        // one wave of the persistent four-instances-per-warp kernel
+        int per_sm = 0, sms = 0;
+        if (cfg->variant == 17) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp8_kernel<17, 6>, 32, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp8_kernel<12, 4>, 32, 0);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        if (e != cudaSuccess || per_sm < 1 || sms < 1) { fail(nullptr, "occupancy query of qp8_kernel", e); mpcb_destroy(h); return -1; }
+        h->qp8_resident = per_sm * sms;
+    }
     double pd[kNP] = {0};
     pd[24] = 2.2 * 9.81;  // reference blastermodel.py:280-282
     cudaMemcpy(h->p_default, pd, sizeof(pd), cudaMemcpyHostToDevice);
@@ -511,7 +514,7 @@ int mpcb_destroy(mpcb_handle *h)
     cudaSetDevice(h->device);
     cudaFree(h->X); cudaFree(h->U); cudaFree(h->ws); cudaFree(h->p_default);
     cudaFree(h->status_scratch); cudaFree(h->iters_scratch); cudaFree(h->xn_scratch); cudaFree(h->u0_scratch);
-    cudaFree(h->d_stage);
+    cudaFree(h->d_stage); cudaFree(h->qp8_next);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);

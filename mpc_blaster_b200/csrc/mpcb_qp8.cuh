@@ -291,32 +291,32 @@ MPCB_DEV void qp8_forward(const Params &P, Qp8Group<NX, NU> &sm, GrpPipe &pipe, 
     acc2_out = grp_sum(acc2);
 }
 
-// The whole QP solve of the four instances of a warp.  `act`: this lane's group holds a real
-// instance (the last warp of a chunk may be partly empty).  Pointers are those of the lane's own
-// instance.  Returns status / iterations of the lane's instance (uniform within a group).
+// What the groups of a warp draw their instances from: one chunk of a batch (instances inst0 .. inst0+B-1
+// of the persistent iterate, chunk-local workspace records) and the chunk's work counter.
+struct Qp8Batch {
+    double *X, *U;             // persistent iterate of the whole batch
+    const double *x0, *yref;
+    size_t yref_stride;        // doubles between the yref of consecutive instances (0: shared)
+    int yps;                   // yref is per stage
+    double *ws;                // workspace of the chunk, linearised by K1
+    double *u0;                // optional outputs (whole batch)
+    int32_t *status, *iters;
+    int inst0, B;
+    unsigned *next;            // work counter of the chunk (zero at launch)
+};
+
+// QP data and cold start of one instance (see F0 in mpcb_qp.cuh), for the groups with `act` set;
+// warp-uniform control flow, so the group reductions at the end are executed by every lane.
 template <int NX, int NU>
-MPCB_DEV int qp8_solve_warp(const Params &P, Qp8Smem<NX, NU> &smw, double *__restrict__ ws, double *__restrict__ Xi,
-                            double *__restrict__ Ui, const double *__restrict__ x0, const double *__restrict__ yref, int yps, bool act,
-                            int *iters_out)
+MPCB_DEV void qp8_setup(const Params &P, double *__restrict__ ws, const double *__restrict__ Xi, const double *__restrict__ Ui,
+                        const double *__restrict__ x0, const double *__restrict__ yref, int yps, bool act, double &est_g, double &est_b,
+                        double &est_d)
 {
     using L = Layout<NX, NU>;
     constexpr int NZ = L::NZ, NT = (NZ + kLPI - 1) / kLPI, NXT = (NX + kLPI - 1) / kLPI;
-    static_assert(NU <= kLPI, "the input block must fit one row slot");
-    const int lane = lane_id();
-    const int s = lane & (kLPI - 1);
-    Qp8Group<NX, NU> &sm = smw.g[lane >> 3];
+    const int s = lane_id() & (kLPI - 1);
     const int N = P.N;
     const double thr0 = P.ipm_thr0, mu0 = P.ipm_mu0;
-    const double nb = (double)(2 * NU * N + 2 * NX * (N - 1));
-
-    for (int idx = s; idx < L::LXX; idx += kLPI) sm.lxx[idx] = 0.0;
-    GrpPipe pipe;
-    g8_init(pipe, &smw.mbar[lane >> 3], s == 0);
-    int xi[NXT];
-    MPCB_UNROLL
-    for (int t = 0; t < NXT; t++) xi[t] = (s + kLPI * t < NX) ? s + kLPI * t : 0;
-
-    // ---------------- F0: QP data and cold start (see mpcb_qp.cuh)
     double eg = 0.0, eb = 0.0, ed = 0.0;
     for (int k = 0; k <= N; k++) {
         double *wk = ws + (size_t)k * L::STAGE;
@@ -368,23 +368,107 @@ MPCB_DEV int qp8_solve_warp(const Params &P, Qp8Smem<NX, NU> &smw, double *__res
             }
         }
     }
-    double est_g = grp_max(eg), est_b = grp_max(eb), est_d = grp_max(ed);
-    double comp = mu0, mu = mu0;
-    int status = ST_MAXITER, iters = P.ipm_max_iter;
-    bool done = !act;
-    pipe_fence();
-    warp_sync();
+    eg = grp_max(eg); eb = grp_max(eb); ed = grp_max(ed);
+    if (act) { est_g = eg; est_b = eb; est_d = ed; }
+}
 
-    for (int it = 0; it < P.ipm_max_iter; it++) {
-        if (!done) {
-            if (!(est_g == est_g) || !(est_b == est_b) || !(mu == mu)) { status = ST_NAN; done = true; iters = it; }
-            else if (mu > kMuDiverge * mu0) { status = ST_MINSTEP; done = true; iters = it; }
-            else if (est_g <= P.tol_stat && est_b <= P.tol_eq && est_d <= P.tol_ineq && comp <= P.tol_comp) {
-                status = ST_OK; done = true; iters = it;
+// The QP solves of a chunk, by one warp: every 8-lane group draws instances from the chunk's work
+// counter, solves them one after the other, and is refilled at an IPM-iteration boundary as soon as
+// its instance ends ("continuous batching").  The four groups of a warp execute the same instruction
+// stream, so without the refill a warp would run for the slowest of its four instances (mean of the
+// maximum of four iteration counts: 12.3 against a mean of 10.8 on the QUAD12 bench batch, +13.5 %).
+// Results do not depend on which group solves an instance.
+template <int NX, int NU>
+MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Batch &job)
+{
+    using L = Layout<NX, NU>;
+    constexpr int NZ = L::NZ, NT = (NZ + kLPI - 1) / kLPI, NXT = (NX + kLPI - 1) / kLPI;
+    static_assert(NU <= kLPI, "the input block must fit one row slot");
+    const int lane = lane_id();
+    const int s = lane & (kLPI - 1);
+    Qp8Group<NX, NU> &sm = smw.g[lane >> 3];
+    const int N = P.N;
+    const double mu0 = P.ipm_mu0;
+    const double nb = (double)(2 * NU * N + 2 * NX * (N - 1));
+
+    for (int idx = s; idx < L::LXX; idx += kLPI) sm.lxx[idx] = 0.0;
+    GrpPipe pipe;
+    g8_init(pipe, &smw.mbar[lane >> 3], s == 0);
+    int xi[NXT];
+    MPCB_UNROLL
+    for (int t = 0; t < NXT; t++) xi[t] = (s + kLPI * t < NX) ? s + kLPI * t : 0;
+
+    // the group's instance in flight (pointers stay valid when there is none: nothing is accessed through them then)
+    double *__restrict__ ws = job.ws;
+    double *__restrict__ Xi = job.X + (size_t)job.inst0 * (N + 1) * NX;
+    double *__restrict__ Ui = job.U + (size_t)job.inst0 * N * NU;
+    const double *__restrict__ x0 = job.x0 + (size_t)job.inst0 * NX;
+    const double *__restrict__ yref = job.yref;
+    int inst = job.inst0;
+    bool has = false, done = false, drained = false;
+    double est_g = 0.0, est_b = 0.0, est_d = 0.0;
+    double comp = mu0, mu = mu0;
+    int status = ST_MAXITER, git = 0;  // git: IPM iterations of the instance in flight
+
+    for (;;) {
+        // ---- the stopping tests of mpcb_qp.cuh, in the same order (an instance that uses up its iterations is not tested again)
+        auto test = [&]() {
+            if (has && !done) {
+                if (git >= P.ipm_max_iter) { status = ST_MAXITER; done = true; }
+                else if (!(est_g == est_g) || !(est_b == est_b) || !(mu == mu)) { status = ST_NAN; done = true; }
+                else if (mu > kMuDiverge * mu0) { status = ST_MINSTEP; done = true; }
+                else if (est_g <= P.tol_stat && est_b <= P.tol_eq && est_d <= P.tol_ineq && comp <= P.tol_comp) { status = ST_OK; done = true; }
             }
+        };
+        test();
+        // ---- retire: RTI update X += dx, U += du (full step); a failed QP leaves the iterate untouched
+        if (has && done) {
+            if (status == ST_OK) {
+                for (int k = 0; k <= N; k++) {
+                    const double *wk = ws + (size_t)k * L::STAGE;
+                    MPCB_UNROLL
+                    for (int t = 0; t < NT; t++) {
+                        const int row = s + kLPI * t;
+                        if (row >= NZ) continue;
+                        if (row < NU) { if (k < N) Ui[(size_t)k * NU + row] += wk[L::O_Z + row]; }
+                        else Xi[(size_t)k * NX + row - NU] += wk[L::O_Z + row];
+                    }
+                }
+            }
+            if (s == 0) {
+                if (job.status) job.status[inst] = status;
+                if (job.iters) job.iters[inst] = git;
+            }
+            if (job.u0 && s < NU) job.u0[(size_t)inst * NU + s] = Ui[s];  // Ui[s] was updated by this very lane
+            has = false;
         }
-        if (!warp_or(done ? 0 : 1)) break;
-        const bool run = !done;
+        // ---- refill from the chunk's work counter
+        const bool want = !has && !drained;
+        if (warp_or(want ? 1 : 0)) {
+            int idx = 0;
+            if (want && s == 0) idx = (int)queue_take(job.next);
+            idx = warp_shfl(idx, lane & ~(kLPI - 1));
+            const bool fresh = want && idx < job.B;
+            if (want && !fresh) drained = true;
+            if (fresh) {
+                inst = job.inst0 + idx;
+                ws = job.ws + (size_t)idx * L::instance_stride(N);
+                Xi = job.X + (size_t)inst * (N + 1) * NX;
+                Ui = job.U + (size_t)inst * N * NU;
+                x0 = job.x0 + (size_t)inst * NX;
+                yref = job.yref + (size_t)inst * job.yref_stride;
+            }
+            qp8_setup<NX, NU>(P, ws, Xi, Ui, x0, yref, job.yps, fresh, est_g, est_b, est_d);
+            if (fresh) { comp = mu0; mu = mu0; status = ST_MAXITER; git = 0; has = true; done = false; }
+            pipe_fence();  // the QP data written above is fetched by bulk copies
+            warp_sync();
+            test();        // an instance that needs no iteration at all ends here (retired at the next trip)
+        }
+        if (!warp_or(has ? 1 : 0)) break;
+        const bool run = has && !done;
+        if (!warp_or(run ? 1 : 0)) continue;
+        const int yps = job.yps;
+        (void)yps;
 
         // ================= S1: backward sweep -- residuals, factorisation, affine right-hand side
         double last_sig = 1.0;
@@ -663,8 +747,8 @@ MPCB_DEV int qp8_solve_warp(const Params &P, Qp8Smem<NX, NU> &smw, double *__res
         warp_sync();
         // a breakdown (NaN) anywhere in the recursion propagates into the last pivot of stage 0
         const bool qpfail = grp_max((last_sig == last_sig && fabs(last_sig) < HUGE_VAL) ? 0.0 : 1.0) > 0.0;
-        if (run && qpfail) { status = ST_QPFAIL; done = true; iters = it; }
-        const bool run2 = !done;
+        if (run && qpfail) { status = ST_QPFAIL; done = true; }
+        const bool run2 = has && !done;
 
         // ================= S2: forward sweep, affine step
         double a_aff, mu_aff, sigmu;
@@ -811,31 +895,14 @@ MPCB_DEV int qp8_solve_warp(const Params &P, Qp8Smem<NX, NU> &smw, double *__res
             est_g *= (1.0 - alpha);
             est_b *= (1.0 - alpha);
             est_d *= (1.0 - alpha);
+            git++;
             if (!(alpha >= P.alpha_min)) {
                 status = (alpha == alpha) ? ST_MINSTEP : ST_NAN;
                 done = true;
-                iters = it + 1;
             }
         }
         warp_sync();
     }
-
-    // ---------------- RTI update: X += dx, U += du (full step); a failed QP leaves the iterate untouched
-    warp_sync();
-    if (act && status == ST_OK) {
-        for (int k = 0; k <= N; k++) {
-            const double *wk = ws + (size_t)k * L::STAGE;
-            MPCB_UNROLL
-            for (int t = 0; t < NT; t++) {
-                const int row = s + kLPI * t;
-                if (row >= NZ) continue;
-                if (row < NU) { if (k < N) Ui[(size_t)k * NU + row] += wk[L::O_Z + row]; }
-                else Xi[(size_t)k * NX + row - NU] += wk[L::O_Z + row];
-            }
-        }
-    }
-    *iters_out = iters;
-    return status;
 }
 
 }  // namespace mpcb

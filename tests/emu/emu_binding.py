@@ -109,11 +109,12 @@ def poc(euler, motor, position, V=150.0, drag=1.0, mode=0):
 
 
 def rti_solve4(P, X, U, x0, yref, p, **opts):
-    """One emulated RTI iteration of up to four instances in one warp (mpcb_qp8.cuh).
+    """One emulated RTI iteration of nb instances by ONE warp of the four-instances-per-warp kernel
+    (mpcb_qp8.cuh): its four groups draw the instances from a work counter and are refilled as they finish.
     X[nb,N+1,nx], U[nb,N,nu] are updated in place; returns (status[nb], iters[nb])."""
     o = make_params(P, **opts)
     nb = X.shape[0]
-    assert 1 <= nb <= 4 and X.flags.c_contiguous and U.flags.c_contiguous
+    assert nb >= 1 and X.flags.c_contiguous and U.flags.c_contiguous
     x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(nb, P.nx)
     yref = np.ascontiguousarray(yref, dtype=np.float64).reshape(nb, P.nx + P.nu)
     p = np.ascontiguousarray(p, dtype=np.float64)

@@ -93,7 +93,7 @@ extern "C" void emu_poc(const double *e, const double *m, const double *pos, dou
 }
 
 // Four instances per warp (mpcb_qp8.cuh).  X[nb][(N+1)*NX], U[nb][N*NU], x0[nb][NX], yref[nb][NY] (shared over stages), p[25];
-// nb <= 4 instances: groups beyond nb are inactive.
+// fewer than 4 instances: the other groups stay idle; more than 4: groups are refilled as their instances end.
 template <int NX, int NU>
 static void rti_four(const Params &P, int nb, double *X, double *U, const double *x0, const double *yref, const double *p, int *status,
                      int *iters)
@@ -112,15 +112,12 @@ static void rti_four(const Params &P, int nb, double *X, double *U, const double
         }
     static Qp8Smem<NX, NU> sm;
     memset(&sm, 0, sizeof(sm));
-    emu::run_warp([&]() {
-        int g = emu::lane() >> 3;
-        const bool act = g < nb;
-        if (!act) g = nb - 1;
-        int my_it = 0;
-        int st = qp8_solve_warp<NX, NU>(P, sm, ws.data() + g * stride, X + (size_t)g * (N + 1) * NX, U + (size_t)g * N * NU,
-                                        x0 + (size_t)g * NX, yref + (size_t)g * (NX + NU), 0, act, &my_it);
-        if (act && (emu::lane() & 7) == 0) { status[g] = st; iters[g] = my_it; }
-    });
+    // the warp's four groups draw the nb instances from a work counter (nb > 4: groups are refilled)
+    unsigned next = 0;
+    Qp8Batch job;
+    job.X = X; job.U = U; job.x0 = x0; job.yref = yref; job.yref_stride = NX + NU; job.yps = 0;
+    job.ws = ws.data(); job.u0 = nullptr; job.status = status; job.iters = iters; job.inst0 = 0; job.B = nb; job.next = &next;
+    emu::run_warp([&]() { qp8_solve_queue<NX, NU>(P, sm, job); });
 }
 extern "C" void emu_rti_solve4(const Params *P, int nb, double *X, double *U, const double *x0, const double *yref, const double *p,
                                int *status, int *iters)

@@ -112,11 +112,12 @@ def test_emulated_poc_generator_matches_oracle_and_reference_golden():
         assert np.abs(Jm_a - Jm).max() < 2e-3 and np.abs(Je_a - Je).max() < 2e-3 and np.abs(Jp_a - Jp).max() < 2e-3
 
 
-@pytest.mark.parametrize("variant,N,nb", [(17, 10, 4), (12, 10, 4), (17, 6, 3), (12, 5, 1)])
+@pytest.mark.parametrize("variant,N,nb", [(17, 10, 4), (12, 10, 4), (17, 6, 3), (12, 5, 1), (12, 8, 11), (17, 5, 9)])
 def test_emulated_four_instances_per_warp_kernel_matches_oracle(variant, N, nb):
     """mpcb_qp8.cuh (four instances per warp, eight lanes each) compiled for the host: full and
     partly filled warps, two RTI steps (the four instances then differ in their IPM iteration
-    counts, so groups finish at different times), against the C oracle."""
+    counts, so groups finish at different times), against the C oracle.  nb > 4: the warp's groups
+    are refilled from the work counter as their instances end (continuous batching)."""
     P = bo.canonical_problem(N, variant)
     x0, yref = sc.random_setpoints(nb, seed=31, nx=P.nx, nu=P.nu)
     p = bo.default_params()
