@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Turn the raw ncu outputs of a round (gpurun_out/) into the tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py <round-tag> <launches.csv> <full.ncu-rep>
+    python tools/summarize_profiles.py <tag> <launches.csv> <full.ncu-rep> ["workload text"] [--bench]
+
+--bench: the capture is of bench.py's own workload (configs[1]); only then is profiles/qp_kernel_traffic.json,
+the per-launch DRAM traffic bench.py reports as roofline.traffic, rewritten.
 """
 import csv
 import io
@@ -25,7 +28,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def main():
-    tag, launches, rep = sys.argv[1:4]
+    args = [a for a in sys.argv[1:] if a != "--bench"]
+    is_bench = "--bench" in sys.argv[1:]
+    tag, launches, rep = args[:3]
+    workload = args[3] if len(args) > 3 else "B=1,024, N=20, BLASTER17"
     out_dir = os.path.join(ROOT, "profiles")
     os.makedirs(out_dir, exist_ok=True)
     # ---- launch list
@@ -62,7 +68,7 @@ def main():
     hdr = rr[0]
     traffic = {}
     with open(os.path.join(out_dir, f"{tag}_ncu_summary.md"), "w") as f:
-        f.write(f"# {tag}: `ncu --set full --clock-control none` of the two hot kernels (B=1,024, N=20, BLASTER17)\n\n")
+        f.write(f"# {tag}: `ncu --set full --clock-control none` of the two hot kernels ({workload})\n\n")
         for r in rr[2:]:
             name = r[hdr.index("Kernel Name")].split("(")[0]
             f.write(f"## `{name}`\n\n| metric | unit | value |\n|---|---|---:|\n")
@@ -78,9 +84,10 @@ def main():
             tb = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
             traffic[name] = tb
             f.write(f"\nDRAM traffic per launch: {tb / 1e6:.1f} MB\n\n")
-    qp = next(v for k, v in traffic.items() if "qp_kernel" in k)
-    json.dump({"kernel": "qp_kernel<17,6,1>", "dram_bytes_per_launch": qp, "source": f"profiles/{tag}_ncu_summary.md",
-               "workload": "B=1024, N=20, BLASTER17"}, open(os.path.join(out_dir, "qp_kernel_traffic.json"), "w"), indent=1)
+    if is_bench:
+        qp = next(v for k, v in traffic.items() if "qp_kernel" in k)
+        json.dump({"kernel": "qp_kernel<17,6,1>", "dram_bytes_per_launch": qp, "source": f"profiles/{tag}_ncu_summary.md",
+                   "workload": workload}, open(os.path.join(out_dir, "qp_kernel_traffic.json"), "w"), indent=1)
     print(open(os.path.join(out_dir, f"{tag}_launches.md")).read())
     print(open(os.path.join(out_dir, f"{tag}_ncu_summary.md")).read()[:3000])
 
