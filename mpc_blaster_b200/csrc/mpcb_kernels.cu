@@ -489,6 +489,9 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         if (e != cudaSuccess || per_sm < 1 || sms < 1) { fail(nullptr, "occupancy query of qp8_kernel", e); mpcb_destroy(h); return -1; }
         h->qp8_resident = per_sm * sms;
+        // test hook: a smaller grid makes the groups of a warp go through many instances
+        const char *qw = getenv("MPCB_QP8_WARPS");
+        if (qw && atoi(qw) >= 1 && atoi(qw) < h->qp8_resident) h->qp8_resident = atoi(qw);
     }
     double pd[kNP] = {0};
     pd[24] = 2.2 * 9.81;  // reference blastermodel.py:280-282

@@ -496,6 +496,34 @@ def test_four_instances_per_warp_kernel_matches_c_oracle(cuda_device, variant, N
         x = co.plant_step(P, x, uo)
 
 
+@pytest.mark.parametrize("variant,N,B,warps", [(12, 20, 301, 3), (17, 10, 77, 2), (12, 8, 9, 1)])
+def test_four_instances_per_warp_kernel_refills_its_groups(cuda_device, variant, N, B, warps, monkeypatch):
+    """Continuous batching of mpcb_qp8.cuh on the GPU: the persistent grid is capped to a few warps
+    (MPCB_QP8_WARPS), so every 8-lane group solves many instances one after the other and is refilled
+    at IPM-iteration boundaries while its neighbours are in the middle of their solves.  Results must
+    not depend on that: same status, iteration counts and iterates as the C oracle, bit-identical to
+    the same kernel run with one instance per group."""
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.random_setpoints(B, seed=78, nx=P.nx, nu=P.nu)
+    trim = sc.hover_trim(P.nu)
+    monkeypatch.setenv("MPCB_QP8_BATCH", "1")
+    monkeypatch.setenv("MPCB_QP8_WARPS", str(warps))
+    few = _mpc(N, B, variant)
+    monkeypatch.delenv("MPCB_QP8_WARPS")
+    wide = _mpc(N, B, variant)
+    orc = co.BatchRTI(P, B)
+    for m in (few, wide, orc):
+        m.reset(x0, trim)
+    uf, Xf, Uf, stf = few.solve(x0, yref)
+    uw, Xw, Uw, stw = wide.solve(x0, yref)
+    uo, Xo, Uo, sto = orc.solve(x0, yref)
+    assert (stf.cpu().numpy() == sto).all() and (few.iters.cpu().numpy() == orc.iters).all()
+    ok = sto == 0
+    assert ok.mean() > 0.95
+    assert np.abs(Uf.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(Xf.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+    assert torch.equal(Uf, Uw) and torch.equal(Xf, Xw) and torch.equal(uf, uw) and torch.equal(stf, stw)
+
+
 def test_quad12_default_scheduler_mixes_both_qp_kernels(cuda_device):
     """QUAD12 with the default scheduler settings: chunks of >= 4,096 instances go to the
     four-instances-per-warp kernel, the remainder chunk to the one-instance kernel; a batch size that

@@ -18,8 +18,8 @@ for var in (17, 12):
     x0, yref = sc.random_setpoints(1, seed=3, nx=P.nx, nu=P.nu)
     X = np.repeat(x0, 6, axis=0).copy(); U = np.tile(sc.hover_trim(P.nu), (5, 1)).copy()
     print(var, eb.rti_solve(P, X, U, x0[0], yref[0], bo.default_params())[:2])
-    # four instances per warp (mpcb_qp8.cuh): a full warp and a partly filled one
-    for nb in (4, 3):
+    # four instances per warp (mpcb_qp8.cuh): a full warp, a partly filled one, and one whose groups are refilled
+    for nb in (4, 3, 9):
         x0, yref = sc.random_setpoints(nb, seed=4, nx=P.nx, nu=P.nu)
         X = np.repeat(x0[:, None, :], 6, axis=1).copy(); U = np.tile(sc.hover_trim(P.nu), (nb, 5, 1)).copy()
         print(var, 'qp8', nb, eb.rti_solve4(P, X, U, x0, yref, bo.default_params()))

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck): 8 instances, N=6, both
-model variants, one solve each plus plant step, cost and command map."""
+model variants, one solve each plus plant step, cost and command map; then the four-instances-per-warp kernel with
+refilled groups."""
 import os
 import sys
 
@@ -20,4 +21,15 @@ for variant in (17, 12):
     q, t = mpc.command_map(X[:, 0], u0) if variant == 17 else (None, None)
     torch.cuda.synchronize()
     print(variant, st.tolist(), mpc.iters.tolist(), float(c.sum()))
+# four-instances-per-warp kernel, one persistent warp: its groups are refilled from the work counter
+os.environ["MPCB_QP8_BATCH"] = "1"
+os.environ["MPCB_QP8_WARPS"] = "1"
+for variant in (17, 12):
+    nx, nu = (17, 6) if variant == 17 else (12, 4)
+    x0, yref = sc.random_setpoints(11, seed=5, nx=nx, nu=nu)
+    mpc = BlasterMPC.canonical(N=5, batch=11, variant=variant)
+    mpc.reset(x0, sc.hover_trim(nu))
+    u0, X, U, st = mpc.solve(x0, yref)
+    torch.cuda.synchronize()
+    print("qp8", variant, st.tolist(), mpc.iters.tolist())
 print("done")
