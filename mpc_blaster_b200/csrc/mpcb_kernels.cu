@@ -346,6 +346,9 @@ Params make_params(const mpcb_config &c)
 }
 
 constexpr int kWPB = 1;  // warps (= instances) per CTA of the QP kernel
+#ifndef MPCB_TP_MINB
+#define MPCB_TP_MINB 12  // resident CTAs per SM the throughput variant of the QP kernel is compiled for
+#endif
 
 template <int NX, int NU>
 int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
@@ -369,7 +372,7 @@ int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, in
             qp8_kernel<NX, NU><<<grid, 32, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb, h->qp8_next);
         }
         else if (nb >= h->throughput_batch)
-            qp_kernel<NX, NU, kWPB, 1, 12><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+            qp_kernel<NX, NU, kWPB, 1, MPCB_TP_MINB><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
                                                                                              h->ws, u0, status, iters, i0, nb);
         else
             qp_kernel<NX, NU, kWPB, 2, 1><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,

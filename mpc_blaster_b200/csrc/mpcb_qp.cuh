@@ -204,6 +204,7 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
             if (k + 1 < N) fetch(k + 1, (k + 1) & 1);
         } else {
             fetch(k, 0);
+            if (k + 1 < N) l2_prefetch(wk + L::STAGE, FINAL ? L::STAGE : RUN1, lane == 0);  // next stage's record: HBM -> L2
         }
         pipe_wait(pipe, half);
         warp_sync();
@@ -434,6 +435,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 if (k > 0) fetch1(k - 1, (k - 1) & 1);
             } else {
                 fetch1(k, 0);
+                if (k > 0) l2_prefetch(wk - L::STAGE, L::O_C1, lane == 0);  // next stage's record: HBM -> L2
             }
             pipe_wait(pipe, half);
             warp_sync();
@@ -626,6 +628,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     if (k > 0) fetch3(k - 1, (k - 1) & 1);
                 } else {
                     fetch3(k, 0);
+                    if (k > 0) l2_prefetch(wk - L::STAGE, L::O_DZA, lane == 0);  // next stage's record: HBM -> L2
                 }
                 pipe_wait(pipe, half);
                 warp_sync();

@@ -187,6 +187,7 @@ MPCB_DEV void qp8_forward(const Params &P, Qp8Group<NX, NU> &sm, GrpPipe &pipe, 
         g8_expect(pipe, L::O_Z + (FINAL ? L::LXX : 0), issue);
         g8_copy(pipe, sm.rec, wk, L::O_Z, issue);
         if (FINAL) g8_copy(pipe, sm.lxx, wk + L::STAGE + L::O_LXX, L::LXX, issue);
+        if (k + 1 < N) l2_prefetch(wk + L::STAGE, FINAL ? L::STAGE : L::O_G, issue);  // next stage's record: HBM -> L2
         // this stage's box data of the lane's own rows: in flight beside the bulk copy
         double bz[NT], btl[NT], btu[NT], bll[NT], blu[NT], blb[NT], bub[NT], bdza[NT];
         bool bhb[NT];
@@ -499,6 +500,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
         for (int k = N - 1; k >= 0; k--) {
             double *wk = ws + (size_t)k * L::STAGE;
             double zr[NT], Hd[NT], q[NT];
+            if (k > 0) l2_prefetch(wk - L::STAGE + L::O_Z, L::O_C1 - L::O_Z, issue);  // next stage's vectors: HBM -> L2
             {
                 // the lane's own rows of the stage vectors: all loads in flight beside the bulk copy of [B A]'
                 double vtl[NT], vtu[NT], vll[NT], vlu[NT], vlb[NT], vub[NT], vg[NT], vpi[NT];
@@ -780,6 +782,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                 warp_sync();
                 g8_expect(pipe, L::O_RB, run2 && s == 0);
                 g8_copy(pipe, sm.rec, wk, L::O_RB, run2 && s == 0);
+                if (k > 0) l2_prefetch(wk - L::STAGE, L::O_DZA, run2 && s == 0);  // next stage's record: HBM -> L2
                 g8_wait(pipe, run2);
                 MPCB_UNROLL
                 for (int t = 0; t < NT; t++) {
