@@ -461,11 +461,13 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         // more than ~2 waves of the latency variant (9 warps x 148 SMs): switch to the throughput variant
         const char *tb = getenv("MPCB_THROUGHPUT_BATCH");
         h->throughput_batch = tb ? atoi(tb) : 4096;
-        // four-instances-per-warp kernel: measured faster from ~4,096 instances on for QUAD12 (+11 % there, +17 % at
-        // 16,384, +32 % at 65,536); for BLASTER17 its 36 KB of shared memory per warp leave 6 warps per SM and it
-        // stays ~7 % behind the one-instance kernel, so it is opt-in there (MPCB_QP8_BATCH=<chunk size>).
+        // four-instances-per-warp kernel (persistent, groups refilled from a work counter, next stage's record
+        // prefetched into L2): measured faster than the one-instance kernel from ~2,600 instances on for QUAD12
+        // (576 k against 487 k solves/s at 3,072; 987 k against 621 k at 65,536) and from ~12,000 on for BLASTER17
+        // (380 k against 378 k at 12,288; 401 k against 383 k at 16,384; 439 k against 393 k at 65,536).
+        // MPCB_QP8_BATCH=<chunk size> overrides the threshold.
         const char *q8 = getenv("MPCB_QP8_BATCH");
-        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 12 ? 4096 : (1 << 30));
+        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 12 ? 3072 : 12288);
     }
     const size_t B = (size_t)h->max_batch;
     const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;

@@ -204,7 +204,13 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
             if (k + 1 < N) fetch(k + 1, (k + 1) & 1);
         } else {
             fetch(k, 0);
-            if (k + 1 < N) l2_prefetch(wk + L::STAGE, FINAL ? L::STAGE : RUN1, lane == 0);  // next stage's record: HBM -> L2
+            if (k + 1 < N) {  // the runs the next stage will fetch: HBM -> L2
+                l2_prefetch(wk + L::STAGE, RUN1, lane == 0);
+                if (FINAL) {
+                    l2_prefetch(wk + L::STAGE + L::O_DZA, L::NZP, lane == 0);
+                    l2_prefetch(wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP, lane == 0);
+                }
+            }
         }
         pipe_wait(pipe, half);
         warp_sync();
@@ -435,7 +441,10 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 if (k > 0) fetch1(k - 1, (k - 1) & 1);
             } else {
                 fetch1(k, 0);
-                if (k > 0) l2_prefetch(wk - L::STAGE, L::O_C1, lane == 0);  // next stage's record: HBM -> L2
+                if (k > 0) {  // the runs the next stage will fetch: HBM -> L2
+                    l2_prefetch(wk - L::STAGE, L::BAT, lane == 0);
+                    l2_prefetch(wk - L::STAGE + L::O_Z, RUNB, lane == 0);
+                }
             }
             pipe_wait(pipe, half);
             warp_sync();
@@ -628,7 +637,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     if (k > 0) fetch3(k - 1, (k - 1) & 1);
                 } else {
                     fetch3(k, 0);
-                    if (k > 0) l2_prefetch(wk - L::STAGE, L::O_DZA, lane == 0);  // next stage's record: HBM -> L2
+                    if (k > 0) {  // the runs the next stage will fetch: HBM -> L2
+                        l2_prefetch(wk - L::STAGE, RUN1, lane == 0);
+                        l2_prefetch(wk - L::STAGE + L::O_C1, 2 * L::NZP, lane == 0);
+                        l2_prefetch(wk - L::STAGE + L::O_PV, L::NXP, lane == 0);
+                    }
                 }
                 pipe_wait(pipe, half);
                 warp_sync();

@@ -187,7 +187,13 @@ MPCB_DEV void qp8_forward(const Params &P, Qp8Group<NX, NU> &sm, GrpPipe &pipe, 
         g8_expect(pipe, L::O_Z + (FINAL ? L::LXX : 0), issue);
         g8_copy(pipe, sm.rec, wk, L::O_Z, issue);
         if (FINAL) g8_copy(pipe, sm.lxx, wk + L::STAGE + L::O_LXX, L::LXX, issue);
-        if (k + 1 < N) l2_prefetch(wk + L::STAGE, FINAL ? L::STAGE : L::O_G, issue);  // next stage's record: HBM -> L2
+        if (k + 1 < N) {  // what the next stage will fetch: HBM -> L2
+            l2_prefetch(wk + L::STAGE, L::O_G, issue);
+            if (FINAL) {
+                l2_prefetch(wk + L::STAGE + L::O_DZA, L::NZP, issue);
+                l2_prefetch(wk + 2 * L::STAGE + L::O_LXX, L::LXX + L::NXP, issue);
+            }
+        }
         // this stage's box data of the lane's own rows: in flight beside the bulk copy
         double bz[NT], btl[NT], btu[NT], bll[NT], blu[NT], blb[NT], bub[NT], bdza[NT];
         bool bhb[NT];
@@ -782,7 +788,11 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                 warp_sync();
                 g8_expect(pipe, L::O_RB, run2 && s == 0);
                 g8_copy(pipe, sm.rec, wk, L::O_RB, run2 && s == 0);
-                if (k > 0) l2_prefetch(wk - L::STAGE, L::O_DZA, run2 && s == 0);  // next stage's record: HBM -> L2
+                if (k > 0) {  // what the next stage will fetch: HBM -> L2
+                    l2_prefetch(wk - L::STAGE, L::O_RB, run2 && s == 0);
+                    l2_prefetch(wk - L::STAGE + L::O_C1, 2 * L::NZP, run2 && s == 0);
+                    l2_prefetch(wk - L::STAGE + L::O_PV, L::NXP, run2 && s == 0);
+                }
                 g8_wait(pipe, run2);
                 MPCB_UNROLL
                 for (int t = 0; t < NT; t++) {

@@ -1,0 +1,19 @@
+#!/bin/sh
+# Round profile on the GPU box (run through gpurun):  sh tools/profile_round.sh <tag>
+# 1. bench.py without a profiler (the numbers);  2. its launch list under ncu (shares of the step);
+# 3. one `ncu --set full` capture of the two hot kernels of bench.py;  4. the same for the large-batch
+# kernels (16,384 instances: throughput variant of qp_kernel, persistent qp8_kernel on QUAD12).
+# Raw outputs go to gpurun_out/; tools/summarize_profiles.py turns them into profiles/<tag>_*.md here.
+set -e
+TAG=${1:-r01}
+mkdir -p gpurun_out
+python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 6 --warmup 2 --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 8 -c 2 -f \
+    -o gpurun_out/${TAG}_full python bench.py --steps 6 --warmup 2 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 2 -c 2 -f \
+    -o gpurun_out/${TAG}_qp1_blaster17_16k python tools/sweep.py --points "16384,20,17,rand" > gpurun_out/${TAG}_ncu_16k_17.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp8_kernel' -s 2 -c 2 -f \
+    -o gpurun_out/${TAG}_qp8_quad12_16k python tools/sweep.py --points "16384,20,12,rand" > gpurun_out/${TAG}_ncu_16k_12.log 2>&1
+ls -la gpurun_out
