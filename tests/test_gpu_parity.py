@@ -546,3 +546,66 @@ def test_quad12_default_scheduler_mixes_both_qp_kernels(cuda_device):
     assert ok.mean() > 0.97 and (mpc.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
     assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
     assert np.abs(u0.cpu().numpy()[ok] - uo[ok]).max() < TOL
+
+
+def test_reference_script_configuration_n60_with_poc_jacobians(cuda_device):
+    """The configuration simulation_blaster.py actually runs: N = 60, Tf = 2.0 (:19-20), the parameters
+    p[0:24] produced by Jacobian_POC_Solver(150, 1, 0.000015).initialise() (:37-39, here by the device
+    generator in its reference mode) packed as :67, x0 = 0 and the set-point of :47-48, zero initial
+    iterate, un-shifted warm start.  Six control steps in lock-step with the C oracle."""
+    from mpc_blaster_b200 import BlasterMPC, JacobianPOCSolver
+    N, Tf = 60, 2.0
+    P = bo.canonical_problem(N)
+    assert abs(P.dt - Tf / N) < 1e-15
+    gen = JacobianPOCSolver(150, 1, 0.000015)
+    gen.initialise()
+    J_mot, J_eul, J_pos = gen.getJacobians()
+    assert np.abs(J_mot).max() > 1e-3                      # the jet does reach the ground: non-trivial parameters
+    p = bo.pack_params(J_mot, J_eul, J_pos, 2.2 * 9.81)
+    mpc = BlasterMPC(P.mass, P.J, P.l_x, P.l_y, N, Tf, P.c, np.diag(P.Q), np.diag(P.R), np.diag(P.Qt), 2.2 * 9.81,
+                     np.array([P.lbx, P.ubx]), np.array([P.lbu, P.ubu]), batch=1)
+    orc = co.BatchRTI(P, 1, nthreads=1)
+    x0, yref = bo.canonical_x0_yref()
+    x = x0.reshape(1, 17).copy()
+    for step in range(6):
+        u0, X, U, st = mpc.solve(x, yref.reshape(1, -1), p)
+        uo, Xo, Uo, sto = orc.solve(x, yref.reshape(1, -1), p)
+        assert int(st[0]) == int(sto[0]) == 0 and int(mpc.iters[0]) == int(orc.iters[0])
+        assert np.abs(U.cpu().numpy() - Uo).max() < TOL and np.abs(X.cpu().numpy() - Xo).max() < TOL
+        x = co.plant_step(P, x, uo, p)
+    assert x[0, 2] > 0.05                                  # it climbs towards z = 3.5
+
+
+def test_mavros_script_configuration(cuda_device):
+    """The other configuration the reference ships (mavros_blaster_sim.py:39-48,60-61): N = 30, Tf = 1.0,
+    weaker position/POC weights, heavy swivel-rate weights (R = 1e1), asymmetric velocity bounds
+    (-0.5 .. 0.4 / 0.5 / 1.0 m/s), set-point (0.5, 1.0, 3.5); 64 vehicles around it, two control steps."""
+    from mpc_blaster_b200 import BlasterMPC
+    N, Tf, B = 30, 1.0, 64
+    c = bo.canonical_problem(N)
+    Q = np.array([1e2] * 6 + [5.0] * 3 + [10.0] * 3 + [1e-2] * 2 + [1.0] * 3)
+    R = np.array([5e-2] * 4 + [1e1] * 2)
+    lbx, ubx = c.lbx.copy(), c.ubx.copy()
+    lbx[6:9] = [-0.5, -0.5, -0.5]
+    ubx[6:9] = [0.4, 0.5, 1.0]
+    P = bo.BlasterProblem(mass=c.mass, J=c.J, l_x=c.l_x, l_y=c.l_y, c=c.c, N=N, dt=Tf / N, Q=Q, R=R, Qt=10 * Q,
+                          lbx=lbx, ubx=ubx, lbu=c.lbu, ubu=c.ubu)
+    mpc = BlasterMPC(P.mass, P.J, P.l_x, P.l_y, N, Tf, P.c, np.diag(Q), np.diag(R), np.diag(10 * Q), 2.2 * 9.81,
+                     np.array([lbx, ubx]), np.array([P.lbu, P.ubu]), batch=B)
+    orc = co.BatchRTI(P, B)
+    x0, _ = sc.closed_loop_setpoints(B, seed=12)
+    x0[:, 6:9] = np.clip(x0[:, 6:9], lbx[6:9] + 0.05, ubx[6:9] - 0.05)
+    yref = np.zeros((B, 23))
+    yref[:, 0:3] = [0.5, 1.0, 3.5]
+    trim = sc.hover_trim()
+    mpc.reset(x0, trim)
+    orc.reset(x0, trim)
+    x = x0
+    for step in range(2):
+        u0, X, U, st = mpc.solve(x, yref)
+        uo, Xo, Uo, sto = orc.solve(x, yref)
+        assert (st.cpu().numpy() == sto).all()
+        ok = sto == 0
+        assert ok.mean() > 0.9 and (mpc.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
+        assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+        x = co.plant_step(P, x, uo)
