@@ -528,6 +528,33 @@ def test_four_instances_per_warp_kernel_refills_its_groups(cuda_device, variant,
     assert torch.equal(Uf, Uw) and torch.equal(Xf, Xw) and torch.equal(uf, uw) and torch.equal(stf, stw)
 
 
+def test_four_instances_per_warp_kernel_refill_with_infeasible_instances(cuda_device, monkeypatch):
+    """Random set-points at N = 40 leave ~1.4 % of the linearised QPs infeasible: those
+    instances end early with the min-step status in the middle of a warp whose other groups keep
+    solving, their iterate must stay untouched, and the group must be refilled like any other.
+    2,000 instances through 5 persistent warps, against the C oracle."""
+    N, B = 40, 2000
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(B, seed=4567)
+    trim = sc.hover_trim()
+    monkeypatch.setenv("MPCB_QP8_BATCH", "1")
+    monkeypatch.setenv("MPCB_QP8_WARPS", "5")
+    mpc = _mpc(N, B)
+    orc = co.BatchRTI(P, B)
+    mpc.reset(x0, trim)
+    orc.reset(x0, trim)
+    X_before = mpc.iterate()[0].clone()
+    u0, X, U, st = mpc.solve(x0, yref)
+    uo, Xo, Uo, sto = orc.solve(x0, yref)
+    st = st.cpu().numpy()
+    assert (st == sto).all() and (mpc.iters.cpu().numpy() == orc.iters).all()
+    bad = sto != 0
+    assert 3 <= bad.sum() <= 0.05 * B, bad.sum()           # the scenario does contain infeasible QPs
+    assert torch.equal(X[torch.as_tensor(bad)], X_before[torch.as_tensor(bad)])
+    ok = ~bad
+    assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+
+
 def test_quad12_default_scheduler_mixes_both_qp_kernels(cuda_device):
     """QUAD12 with the default scheduler settings: chunks of >= 3,072 instances go to the
     four-instances-per-warp kernel, the remainder chunk to the one-instance kernel; a batch size that
