@@ -636,3 +636,37 @@ def test_mavros_script_configuration(cuda_device):
         assert ok.mean() > 0.9 and (mpc.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
         assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
         x = co.plant_step(P, x, uo)
+
+
+@pytest.mark.parametrize("qp8", [False, True])
+def test_solve_is_cuda_graph_capturable(cuda_device, qp8, monkeypatch):
+    """SURVEY 8b ownership rule: no allocation and no synchronisation inside mpcb_solve, so a control
+    loop can capture it in a CUDA graph.  Capture one solve (either QP kernel; the persistent kernel's
+    work-counter reset is a memset node), replay it from the same iterate: bit-identical outputs."""
+    N, B = 10, 96
+    if qp8:
+        monkeypatch.setenv("MPCB_QP8_BATCH", "1")
+        monkeypatch.setenv("MPCB_QP8_WARPS", "7")
+    x0, yref = sc.random_setpoints(B, seed=5)
+    x0 = torch.as_tensor(x0, device="cuda")
+    yref = torch.as_tensor(yref, device="cuda")
+    trim = torch.as_tensor(sc.hover_trim(), device="cuda")
+    mpc = _mpc(N, B)
+    mpc.reset(x0, trim)
+    u_e, X_e, U_e, st_e = mpc.solve(x0, yref)
+    torch.cuda.synchronize()
+    mpc.reset(x0, trim)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            u_g, X_g, U_g, st_g = mpc.solve(x0, yref)
+    torch.cuda.current_stream().wait_stream(side)
+    for rep in range(2):
+        mpc.reset(x0, trim)
+        u_g.zero_(); X_g.zero_(); U_g.zero_(); st_g.fill_(-1)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(st_g, st_e) and int((st_e == 0).sum()) >= B - 2
+        assert torch.equal(u_g, u_e) and torch.equal(X_g, X_e) and torch.equal(U_g, U_e)
