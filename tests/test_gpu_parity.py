@@ -670,3 +670,29 @@ def test_solve_is_cuda_graph_capturable(cuda_device, qp8, monkeypatch):
         torch.cuda.synchronize()
         assert torch.equal(st_g, st_e) and int((st_e == 0).sum()) >= B - 2
         assert torch.equal(u_g, u_e) and torch.equal(X_g, X_e) and torch.equal(U_g, U_e)
+
+
+@pytest.mark.parametrize("variant", [12, 17])
+def test_full_size_config5_sample_against_oracle(cuda_device, variant):
+    """BASELINE config 5 at its full size (1,048,576 instances, N = 20, default scheduler: chunks of
+    the workspace budget on the persistent four-instances-per-warp kernel): a random sample of 512
+    instances spread over all chunks against the C oracle -- status, IPM iteration count and u0 --
+    plus the whole-batch convergence rate."""
+    B, N = 1 << 20, 20
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.random_setpoints(B, seed=4567, nx=P.nx, nu=P.nu)
+    trim = sc.hover_trim(P.nu)
+    mpc = _mpc(N, B, variant)
+    mpc.reset(x0, trim)
+    u0, _, _, st = mpc.solve(x0, yref, want_traj=False)
+    assert float((st == 0).double().mean()) > 0.9999
+    idx = np.sort(np.random.default_rng(1).choice(B, 512, replace=False))
+    orc = co.BatchRTI(P, len(idx))
+    orc.reset(x0[idx], trim)
+    uo, _, _, sto = orc.solve(x0[idx], yref[idx])
+    ti = torch.as_tensor(idx, device="cuda")
+    assert (st[ti].cpu().numpy() == sto).all() and (mpc.iters[ti].cpu().numpy() == orc.iters).all()
+    ok = sto == 0
+    assert np.abs(u0[ti].cpu().numpy()[ok] - uo[ok]).max() < TOL
+    del mpc
+    torch.cuda.empty_cache()
