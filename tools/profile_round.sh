@@ -2,7 +2,7 @@
 # Round profile on the GPU box (run through gpurun):  sh tools/profile_round.sh <tag>
 # 1. bench.py without a profiler (the numbers);  2. its launch list under ncu (shares of the step);
 # 3. one `ncu --set full` capture of the two hot kernels of bench.py;  4. the same for the large-batch
-# kernels (16,384 instances: throughput variant of qp_kernel, persistent qp8_kernel on QUAD12).
+# kernels (16,384 instances: throughput variant of qp_kernel, persistent qp8_kernel on both models).
 # Raw outputs go to gpurun_out/; tools/summarize_profiles.py turns them into profiles/<tag>_*.md here.
 set -e
 TAG=${1:-r01}
@@ -12,8 +12,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 6 --warmup 2 --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 8 -c 2 -f \
     -o gpurun_out/${TAG}_full python bench.py --steps 6 --warmup 2 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 2 -c 2 -f \
+# large batches: the one-instance throughput variant (forced: chunks of this size default to qp8_kernel), then qp8_kernel on both models
+MPCB_QP8_BATCH=1000000000 ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 2 -c 2 -f \
     -o gpurun_out/${TAG}_qp1_blaster17_16k python tools/sweep.py --points "16384,20,17,rand" > gpurun_out/${TAG}_ncu_16k_17.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'qp8_kernel' -s 1 -c 1 -f \
+    -o gpurun_out/${TAG}_qp8_blaster17_16k python tools/sweep.py --points "16384,20,17,rand" > gpurun_out/${TAG}_ncu_16k_17_qp8.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp8_kernel' -s 2 -c 2 -f \
     -o gpurun_out/${TAG}_qp8_quad12_16k python tools/sweep.py --points "16384,20,12,rand" > gpurun_out/${TAG}_ncu_16k_12.log 2>&1
 ls -la gpurun_out
