@@ -18,7 +18,9 @@
  * _host, pointers are DEVICE pointers on the handle's GPU and the call is asynchronous on
  * `stream` (a cudaStream_t passed as void*; NULL = default stream).  No allocation happens
  * inside mpcb_solve / mpcb_plant_step / mpcb_cost, so they are CUDA-graph capturable.
- * One handle per stream; handles are independent (one per GPU for multi-GPU sharding).
+ * One handle per stream; handles are independent (one per GPU for multi-GPU sharding).  As with any
+ * CUDA library that takes a stream, the caller makes the handle's GPU the current device before a
+ * stream-based call (the _host entry point does it itself).
  *
  * Return value: 0 on success, negative on API misuse or CUDA failure (message through
  * mpcb_last_error).  Per-instance solver outcome goes to status[B], mirroring acados'
