@@ -37,6 +37,10 @@ extern "C" {
 
 #define MPCB_VARIANT_BLASTER17 17 /* the reference's model: 17 states / 6 inputs / 25 params */
 #define MPCB_VARIANT_QUAD12 12    /* states 0..11, inputs 0..3, gimbal frozen (north_star sizing) */
+#define MPCB_VARIANT_QUAT13 13    /* QUAD12 with a quaternion attitude: x = [p(3), q(w,x,y,z), v(3), omega(3)], 4 inputs;
+                                     quaternion algebra of reference utils/MathUtils.py:5-54 (which no reference model
+                                     uses); Q/lbx/ubx entries 3..6 belong to q; the iterate must be initialised with
+                                     unit quaternions (mpcb_reset with x_init) -- the all-zero default is not one */
 #define MPCB_NP 25
 #define MPCB_F64 64
 #define MPCB_F32 32

@@ -398,7 +398,7 @@ extern "C" {
 
 int mpcb_config_default(mpcb_config *cfg, int variant, int N)
 {
-    if (!cfg || (variant != 17 && variant != 12) || N < 2) return -1;
+    if (!cfg || (variant != 17 && variant != 12 && variant != 13) || N < 2) return -1;
     memset(cfg, 0, sizeof(*cfg));
     cfg->variant = variant; cfg->N = N; cfg->dt = 2.0 / 60.0;
     cfg->mass = 9.0;
@@ -416,13 +416,25 @@ int mpcb_config_default(mpcb_config *cfg, int variant, int N)
     cfg->ipm_max_iter = 60; cfg->ipm_mu0 = 1e2; cfg->ipm_thr0 = -0.5;
     cfg->tol_stat = 1e-6; cfg->tol_eq = 1e-8; cfg->tol_ineq = 1e-8; cfg->tol_comp = 1e-8; cfg->alpha_min = 1e-8;
     cfg->dtype = MPCB_F64; cfg->max_batch = 1024; cfg->ws_batch = 0; cfg->device = -1;
+    if (variant == 13) {
+        // QUAT13: x = [p, q(w,x,y,z), v, omega].  The Euler weights go to the quaternion components; the Euler boxes
+        // (10, 10, 20 deg) become boxes on the vector part (sine of half the angle), q_w stays near 1.
+        const double hq[3] = {sin(0.174532925 / 2), sin(0.174532925 / 2), sin(0.349066 / 2)};
+        double Q13[13], lb13[13], ub13[13];
+        for (int i = 0; i < 3; i++) { Q13[i] = Q[i]; lb13[i] = lbx[i]; ub13[i] = ubx[i]; }
+        Q13[3] = 1e3; lb13[3] = 0.9; ub13[3] = 1.05;
+        for (int i = 0; i < 3; i++) { Q13[4 + i] = 1e3; lb13[4 + i] = -hq[i]; ub13[4 + i] = hq[i]; }
+        for (int i = 0; i < 6; i++) { Q13[7 + i] = Q[6 + i]; lb13[7 + i] = lbx[6 + i]; ub13[7 + i] = ubx[6 + i]; }
+        for (int i = 0; i < 17; i++) { cfg->Q[i] = cfg->Qt[i] = cfg->lbx[i] = cfg->ubx[i] = 0.0; }
+        for (int i = 0; i < 13; i++) { cfg->Q[i] = Q13[i]; cfg->Qt[i] = 10 * Q13[i]; cfg->lbx[i] = lb13[i]; cfg->ubx[i] = ub13[i]; }
+    }
     return 0;
 }
 
 int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
 {
     if (!cfg || !out) return fail(nullptr, "null argument");
-    if (cfg->variant != 17 && cfg->variant != 12) return fail(nullptr, "variant must be 17 or 12");
+    if (cfg->variant != 17 && cfg->variant != 12 && cfg->variant != 13) return fail(nullptr, "variant must be 17, 12 or 13");
     if (cfg->N < 2 || cfg->N > 4096) return fail(nullptr, "horizon out of range");
     if (cfg->dtype != MPCB_F64)
         return fail(nullptr, "only dtype = MPCB_F64 is implemented (an interior point with active state bounds is not viable in FP32, DESIGN.md)");
@@ -435,7 +447,7 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     if (!h) return fail(nullptr, "out of host memory");
     h->cfg = *cfg;
     h->P = make_params(*cfg);
-    h->nx = cfg->variant == 17 ? 17 : 12;
+    h->nx = cfg->variant == 17 ? 17 : cfg->variant == 13 ? 13 : 12;
     h->nu = cfg->variant == 17 ? 6 : 4;
     h->N = cfg->N;
     h->max_batch = cfg->max_batch;
@@ -446,7 +458,8 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     }
     e = cudaSetDevice(h->device);
     if (e != cudaSuccess) { fail(nullptr, "cudaSetDevice", e); delete h; return -1; }
-    h->ws_stride = cfg->variant == 17 ? Layout<17, 6>::instance_stride(h->N) : Layout<12, 4>::instance_stride(h->N);
+    h->ws_stride = cfg->variant == 17 ? Layout<17, 6>::instance_stride(h->N)
+                   : cfg->variant == 13 ? Layout<13, 4>::instance_stride(h->N) : Layout<12, 4>::instance_stride(h->N);
     int wsb = cfg->ws_batch;
     if (wsb <= 0) {
         // auto: at most ~24 GiB of solver workspace resident at once
@@ -467,7 +480,7 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         // (380 k against 378 k at 12,288; 401 k against 383 k at 16,384; 439 k against 393 k at 65,536).
         // MPCB_QP8_BATCH=<chunk size> overrides the threshold.
         const char *q8 = getenv("MPCB_QP8_BATCH");
-        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 12 ? 3072 : 12288);
+        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 17 ? 12288 : 3072);
     }
     const size_t B = (size_t)h->max_batch;
     const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;
@@ -490,6 +503,7 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         // one wave of the persistent four-instances-per-warp kernel
         int per_sm = 0, sms = 0;
         if (cfg->variant == 17) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp8_kernel<17, 6>, 32, 0);
+        else if (cfg->variant == 13) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp8_kernel<13, 4>, 32, 0);
         else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp8_kernel<12, 4>, 32, 0);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         if (e != cudaSuccess || per_sm < 1 || sms < 1) { fail(nullptr, "occupancy query of qp8_kernel", e); mpcb_destroy(h); return -1; }
@@ -544,6 +558,7 @@ int mpcb_reset(mpcb_handle *h, const double *x_init, const double *u_init, int u
     const size_t per = (size_t)(h->N + 1) * h->nx + (size_t)h->N * h->nu;
     const unsigned grid = (unsigned)((per * B + 255) / 256);
     if (h->nx == 17) reset_kernel<17, 6><<<grid, 256, 0, s>>>(h->P, h->X, h->U, x_init, u_init, u_per_instance, B);
+    else if (h->nx == 13) reset_kernel<13, 4><<<grid, 256, 0, s>>>(h->P, h->X, h->U, x_init, u_init, u_per_instance, B);
     else reset_kernel<12, 4><<<grid, 256, 0, s>>>(h->P, h->X, h->U, x_init, u_init, u_per_instance, B);
     g_launches += 1;
     CK(h, cudaGetLastError());
@@ -559,8 +574,9 @@ int mpcb_solve(mpcb_handle *h, const double *x0, const double *yref, int yref_mo
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!p) { p = h->p_default; p_mode = MPCB_SHARED; }
-    int rc = (h->nx == 17) ? launch_solve_chunks<17, 6>(h, x0, yref, yref_mode, p, p_mode, u0, status, iters, B, s)
-                           : launch_solve_chunks<12, 4>(h, x0, yref, yref_mode, p, p_mode, u0, status, iters, B, s);
+    int rc = (h->nx == 17)   ? launch_solve_chunks<17, 6>(h, x0, yref, yref_mode, p, p_mode, u0, status, iters, B, s)
+             : (h->nx == 13) ? launch_solve_chunks<13, 4>(h, x0, yref, yref_mode, p, p_mode, u0, status, iters, B, s)
+                             : launch_solve_chunks<12, 4>(h, x0, yref, yref_mode, p, p_mode, u0, status, iters, B, s);
     if (rc) return rc;
     if (X) CK(h, cudaMemcpyAsync(X, h->X, (size_t)B * (h->N + 1) * h->nx * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if (U) CK(h, cudaMemcpyAsync(U, h->U, (size_t)B * h->N * h->nu * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -625,6 +641,7 @@ int mpcb_plant_step(mpcb_handle *h, const double *x, const double *u, const doub
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned grid = (B + 127) / 128;
     if (h->nx == 17) plant_kernel<17, 6><<<grid, 128, 0, s>>>(h->P, x, u, p, p_mode, xnext, B);
+    else if (h->nx == 13) plant_kernel<13, 4><<<grid, 128, 0, s>>>(h->P, x, u, p, p_mode, xnext, B);
     else plant_kernel<12, 4><<<grid, 128, 0, s>>>(h->P, x, u, p, p_mode, xnext, B);
     g_launches += 1;
     CK(h, cudaGetLastError());
@@ -649,6 +666,8 @@ int mpcb_closed_loop(mpcb_handle *h, double *x, const double *yref, int yref_mod
         const unsigned grid = (B + 127) / 128;
         if (h->nx == 17)
             loop_book_kernel<17><<<grid, 128, 0, s>>>(x, h->xn_scratch, h->status_scratch, h->iters_scratch, n_fail, iters_sum, B);
+        else if (h->nx == 13)
+            loop_book_kernel<13><<<grid, 128, 0, s>>>(x, h->xn_scratch, h->status_scratch, h->iters_scratch, n_fail, iters_sum, B);
         else
             loop_book_kernel<12><<<grid, 128, 0, s>>>(x, h->xn_scratch, h->status_scratch, h->iters_scratch, n_fail, iters_sum, B);
         g_launches += 1;
@@ -665,6 +684,7 @@ int mpcb_cost(mpcb_handle *h, const double *yref, int yref_mode, double *cost, i
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned grid = (B + 127) / 128;
     if (h->nx == 17) cost_kernel<17, 6><<<grid, 128, 0, s>>>(h->P, h->X, h->U, yref, yref_mode, cost, B);
+    else if (h->nx == 13) cost_kernel<13, 4><<<grid, 128, 0, s>>>(h->P, h->X, h->U, yref, yref_mode, cost, B);
     else cost_kernel<12, 4><<<grid, 128, 0, s>>>(h->P, h->X, h->U, yref, yref_mode, cost, B);
     g_launches += 1;
     CK(h, cudaGetLastError());
@@ -703,6 +723,10 @@ int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BA
             linearize_kernel<17, 6><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
             const size_t per = (size_t)h->N * (23 * 17 + 17);
             debug_copy_kernel<17, 6><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, BAt, b, i0, nb);
+        } else if (h->nx == 13) {
+            linearize_kernel<13, 4><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+            const size_t per = (size_t)h->N * (17 * 13 + 13);
+            debug_copy_kernel<13, 4><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, BAt, b, i0, nb);
         } else {
             linearize_kernel<12, 4><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
             const size_t per = (size_t)h->N * (16 * 12 + 12);
@@ -720,6 +744,7 @@ int mpcb_shift(mpcb_handle *h, int B, void *stream)
     if (B == 0) return 0;
     const unsigned grid = (B + 127) / 128;
     if (h->nx == 17) shift_kernel<17, 6><<<grid, 128, 0, (cudaStream_t)stream>>>(h->P, h->X, h->U, B);
+    else if (h->nx == 13) shift_kernel<13, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(h->P, h->X, h->U, B);
     else shift_kernel<12, 4><<<grid, 128, 0, (cudaStream_t)stream>>>(h->P, h->X, h->U, B);
     g_launches += 1;
     CK(h, cudaGetLastError());
@@ -788,6 +813,7 @@ int mpcb_command_map(mpcb_handle *h, const double *x, const double *u0, double *
 {
     if (check_batch(h, B)) return -1;
     if (!x || (thrust && !u0)) return fail(h, "null argument");
+    if (h->nx == 13) return fail(h, "command mapping takes Euler-angle states (variants 17 and 12); a QUAT13 state already carries the attitude quaternion");
     if (B == 0) return 0;
     command_map_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, u0, h->nx, h->nu, quat, thrust, B);
     g_launches += 1;

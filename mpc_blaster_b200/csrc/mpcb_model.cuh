@@ -6,6 +6,10 @@
 // Input   u = [T0..T3, alpha1_dot, alpha2_dot]                                  (:184-190)
 // Params  p = [vec(J_angles 3x2), vec(J_euler 3x3), vec(J_p 3x3), T_blast]      (:203-210, column-major)
 // QUAD12 = states 0..11 and inputs 0..3 with the gimbal frozen at alpha1 = alpha2 = 0.
+// QUAT13 = QUAD12 with the attitude as a unit quaternion, x = [p(3), q(w,x,y,z), v(3), omega(3)]:
+//          qdot = 1/2 q (x) [0, omega], vdot = R(q) e3 (sum T + T_blast)/M + g with the quaternion algebra of
+//          reference utils/MathUtils.py (quat_mul / quat_to_rot below).  SURVEY 8a row A9; the reference has no
+//          such model, so it is tested against the Euler model and the CPU checkers, not against reference outputs.
 #pragma once
 #include "mpcb_common.cuh"
 
@@ -58,6 +62,7 @@ struct Trig {
 template <int NX, typename T>
 MPCB_DEV void eval_trig(const T *xs, Trig<NX, T> &g)
 {
+    if constexpr (NX == 13) { (void)xs; (void)g; return; }  // quaternion attitude: no trigonometry at all
     const int lane = lane_id();
     T ang = xs[3];
     if (lane == 1) ang = xs[4];
@@ -83,6 +88,7 @@ MPCB_DEV void eval_trig(const T *xs, Trig<NX, T> &g)
 template <int NX, typename T>
 MPCB_DEV void eval_trig_local(const T *xs, Trig<NX, T> &g)
 {
+    if constexpr (NX == 13) { (void)xs; (void)g; return; }
     sincos_(xs[3], &g.sf, &g.cf);
     sincos_(xs[4], &g.st, &g.ct);
     sincos_(xs[5], &g.sp, &g.cp);
@@ -107,6 +113,15 @@ struct StagePoint {
 template <int NX, typename T>
 MPCB_DEV void eval_point(const Trig<NX, T> &g, const T *xs, T Tsum, T Tb, StagePoint<NX, T> &s)
 {
+    if constexpr (NX == 13) {
+        // QUAT13 needs R(q) e3 (third column of quat_to_rot) and the body-z force
+        const T w = xs[3], qx = xs[4], qy = xs[5], qz = xs[6];
+        s.R[0][2] = 2 * (qx * qz + w * qy);
+        s.R[1][2] = 2 * (qy * qz - w * qx);
+        s.R[2][2] = 2 * (w * w + qz * qz) - 1;
+        s.w[2] = Tsum + Tb;
+        return;
+    }
     s.R[0][0] = g.cp * g.ct; s.R[0][1] = g.cp * g.st * g.sf - g.sp * g.cf; s.R[0][2] = g.cp * g.st * g.cf + g.sp * g.sf;
     s.R[1][0] = g.sp * g.ct; s.R[1][1] = g.sp * g.st * g.sf + g.cp * g.cf; s.R[1][2] = g.sp * g.st * g.cf - g.cp * g.sf;
     s.R[2][0] = -g.st;       s.R[2][1] = g.ct * g.sf;                      s.R[2][2] = g.ct * g.cf;
@@ -128,6 +143,33 @@ MPCB_DEV void eval_point(const Trig<NX, T> &g, const T *xs, T Tsum, T Tb, StageP
 template <int NX, int NU, typename T>
 MPCB_DEV void eval_f(const Params &P, const StagePoint<NX, T> &s, const T *xs, const T *u, const T *pp, T *xd)
 {
+    if constexpr (NX == 13) {
+        const T w = xs[3], qx = xs[4], qy = xs[5], qz = xs[6];
+        const T *v = xs + 7, *om = xs + 10;
+        xd[0] = v[0]; xd[1] = v[1]; xd[2] = v[2];
+        // qdot = 1/2 q (x) [0, omega]  (quat_mul with a zero scalar part)
+        xd[3] = T(0.5) * (-qx * om[0] - qy * om[1] - qz * om[2]);
+        xd[4] = T(0.5) * (w * om[0] + qy * om[2] - qz * om[1]);
+        xd[5] = T(0.5) * (w * om[1] - qx * om[2] + qz * om[0]);
+        xd[6] = T(0.5) * (w * om[2] + qx * om[1] - qy * om[0]);
+        const T F = (T)P.inv_mass * s.w[2];
+        xd[7] = F * s.R[0][2]; xd[8] = F * s.R[1][2]; xd[9] = F * s.R[2][2] - (T)kGravity;
+        T Jo[3], cr[3];
+        MPCB_UNROLL
+        for (int i = 0; i < 3; i++) Jo[i] = (T)P.J[3 * i] * om[0] + (T)P.J[3 * i + 1] * om[1] + (T)P.J[3 * i + 2] * om[2];
+        cr[0] = om[1] * Jo[2] - om[2] * Jo[1];
+        cr[1] = om[2] * Jo[0] - om[0] * Jo[2];
+        cr[2] = om[0] * Jo[1] - om[1] * Jo[0];
+        MPCB_UNROLL
+        for (int i = 0; i < 3; i++) {
+            T a = -((T)P.Jinv[3 * i] * cr[0] + (T)P.Jinv[3 * i + 1] * cr[1] + (T)P.Jinv[3 * i + 2] * cr[2]);
+            MPCB_UNROLL
+            for (int j = 0; j < 4; j++) a += (T)P.JinvG[4 * i + j] * u[j];
+            xd[(10 + i) < NX ? 10 + i : 0] = a;
+        }
+        (void)pp;
+        return;
+    }
     const T *v = xs + 6, *om = xs + 9;
     xd[0] = v[0]; xd[1] = v[1]; xd[2] = v[2];
     xd[3] = s.ed[0]; xd[4] = s.ed[1]; xd[5] = s.ed[2];
@@ -167,6 +209,41 @@ template <int NX, int NU, typename T>
 MPCB_DEV void eval_jac_col(const Params &P, const Trig<NX, T> &g, const StagePoint<NX, T> &s, const T *xs, const T *pp,
                            T Tb, const T *S, int ucol, T *K)
 {
+    if constexpr (NX == 13) {
+        const T w = xs[3], qx = xs[4], qy = xs[5], qz = xs[6];
+        const T *om = xs + 10;
+        const T *Sq = S + 3, *So = S + 10;
+        K[0] = S[7]; K[1] = S[8]; K[2] = S[9];
+        // d(qdot) = 1/2 (dq (x) [0, omega] + q (x) [0, domega])
+        K[3] = T(0.5) * (-om[0] * Sq[1] - om[1] * Sq[2] - om[2] * Sq[3] - qx * So[0] - qy * So[1] - qz * So[2]);
+        K[4] = T(0.5) * (om[0] * Sq[0] + om[2] * Sq[2] - om[1] * Sq[3] + w * So[0] - qz * So[1] + qy * So[2]);
+        K[5] = T(0.5) * (om[1] * Sq[0] - om[2] * Sq[1] + om[0] * Sq[3] + qz * So[0] + w * So[1] - qx * So[2]);
+        K[6] = T(0.5) * (om[2] * Sq[0] + om[1] * Sq[1] - om[0] * Sq[2] - qy * So[0] + qx * So[1] + w * So[2]);
+        // d(vdot) = F d(R e3)/dq dq + (R e3 / M) dT
+        const T m = (T)P.inv_mass, F2 = 2 * m * s.w[2];
+        const T thr = (ucol >= 0 && ucol < 4) ? m : T(0);
+        K[7] = F2 * (qy * Sq[0] + qz * Sq[1] + w * Sq[2] + qx * Sq[3]) + thr * s.R[0][2];
+        K[8] = F2 * (-qx * Sq[0] - w * Sq[1] + qz * Sq[2] + qy * Sq[3]) + thr * s.R[1][2];
+        K[9] = F2 * (2 * w * Sq[0] + 2 * qz * Sq[3]) + thr * s.R[2][2];
+        T Jo[3], JS[3], c1v[3], c2v[3];
+        MPCB_UNROLL
+        for (int i = 0; i < 3; i++) {
+            Jo[i] = (T)P.J[3 * i] * om[0] + (T)P.J[3 * i + 1] * om[1] + (T)P.J[3 * i + 2] * om[2];
+            JS[i] = (T)P.J[3 * i] * So[0] + (T)P.J[3 * i + 1] * So[1] + (T)P.J[3 * i + 2] * So[2];
+        }
+        c1v[0] = om[1] * JS[2] - om[2] * JS[1]; c1v[1] = om[2] * JS[0] - om[0] * JS[2]; c1v[2] = om[0] * JS[1] - om[1] * JS[0];
+        c2v[0] = Jo[1] * So[2] - Jo[2] * So[1]; c2v[1] = Jo[2] * So[0] - Jo[0] * So[2]; c2v[2] = Jo[0] * So[1] - Jo[1] * So[0];
+        MPCB_UNROLL
+        for (int i = 0; i < 3; i++) {
+            T a = T(0);
+            MPCB_UNROLL
+            for (int k = 0; k < 3; k++) a -= (T)P.Jinv[3 * i + k] * (c1v[k] - c2v[k]);
+            if (ucol >= 0 && ucol < 4) a += (T)P.JinvG[4 * i + ucol];
+            K[(10 + i) < NX ? 10 + i : 0] = a;
+        }
+        (void)g; (void)pp; (void)Tb;
+        return;
+    }
     const T *om = xs + 9;
     const T m = (T)P.inv_mass;
     K[0] = S[6]; K[1] = S[7]; K[2] = S[8];

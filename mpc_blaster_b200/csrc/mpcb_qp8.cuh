@@ -36,7 +36,8 @@ struct Qp8Group {
     static constexpr int kBody = L::O_Z + L::LXX + 2 * L::NXP + 3 * L::NZP + 7 * L::NXP;
     double pad[(4 - kBody % 16 + 16) % 16 == 0 ? 16 : (4 - kBody % 16 + 16) % 16];
 };
-static_assert(sizeof(Qp8Group<17, 6>) % 128 == 32 && sizeof(Qp8Group<12, 4>) % 128 == 32, "group stride must be 32 mod 128 bytes");
+static_assert(sizeof(Qp8Group<17, 6>) % 128 == 32 && sizeof(Qp8Group<12, 4>) % 128 == 32 && sizeof(Qp8Group<13, 4>) % 128 == 32,
+              "group stride must be 32 mod 128 bytes");
 template <int NX, int NU>
 struct Qp8Smem {
     Qp8Group<NX, NU> g[kGPW];

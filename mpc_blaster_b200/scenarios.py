@@ -11,6 +11,21 @@ import numpy as np
 NX_FULL, NU_FULL, NP = 17, 6, 25
 
 
+def to_quat13(x0, yref):
+    """QUAT13 version of a QUAD12 scenario: x = [p, q(w,x,y,z), v, omega] with q the quaternion of
+    Rz(psi) Ry(theta) Rx(phi) (blastermodel.py:122), reference attitude q = [1,0,0,0], u_ref = 0."""
+    x0 = np.asarray(x0, dtype=np.float64)
+    hf, ht, hp = x0[:, 3] / 2, x0[:, 4] / 2, x0[:, 5] / 2
+    cf, sf, ct, st, cp, sp = np.cos(hf), np.sin(hf), np.cos(ht), np.sin(ht), np.cos(hp), np.sin(hp)
+    q = np.stack([cp * ct * cf + sp * st * sf, cp * ct * sf - sp * st * cf, cp * st * cf + sp * ct * sf,
+                  sp * ct * cf - cp * st * sf], axis=1)
+    x13 = np.concatenate([x0[:, 0:3], q, x0[:, 6:12]], axis=1)
+    y = np.zeros(yref.shape[:-1] + (17,))
+    y[..., 0:3] = yref[..., 0:3]
+    y[..., 3] = 1.0
+    return np.ascontiguousarray(x13), y
+
+
 def default_params() -> np.ndarray:
     """blastermodel.py:280-282: POC Jacobians 0, T_blast = 2.2*9.81."""
     p = np.zeros(NP)
@@ -47,6 +62,8 @@ def random_setpoints(B: int, seed: int = 1234, nx: int = 17, nu: int = 6, alpha_
     yref[:, 2] = rng.uniform(0.5, 4.5, B)
     if nx == NX_FULL:
         return x0, yref
+    if nx == 13:
+        return to_quat13(x0, yref)
     y = np.zeros((B, nx + nu))
     y[:, :nx] = yref[:, :nx]
     return np.ascontiguousarray(x0[:, :nx]), y
@@ -55,6 +72,8 @@ def random_setpoints(B: int, seed: int = 1234, nx: int = 17, nu: int = 6, alpha_
 def lemniscate_tracking(B: int, N: int, dt: float = 1.0 / 30, seed: int = 2345, nx: int = 17, nu: int = 6,
                         amp_xy: float = 1.2, amp_z: float = 1.0, period: float = 2.0):
     """Config 3: per-stage yref[B, N+1, ny] on a figure-eight with random phase; x0 on the curve."""
+    if nx == 13:
+        return to_quat13(*lemniscate_tracking(B, N, dt, seed, 12, 4, amp_xy, amp_z, period))
     rng = np.random.default_rng(seed)
     ph = rng.uniform(0, 2 * np.pi, B)
     t = np.arange(N + 1) * dt
@@ -98,6 +117,8 @@ def closed_loop_setpoints(B: int, seed: int = 3456, nx: int = 17, nu: int = 6):
     yref[:, 2] = np.clip(x0[:, 2] + rng.uniform(-1.5, 1.5, B), 0.5, 4.5)
     if nx == NX_FULL:
         return x0, yref
+    if nx == 13:
+        return to_quat13(x0, yref)
     y = np.zeros((B, nx + nu))
     y[:, :nx] = yref[:, :nx]
     return np.ascontiguousarray(x0[:, :nx]), y

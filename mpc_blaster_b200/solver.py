@@ -102,7 +102,8 @@ class BlasterMPC:
     """B independent BLASTER controllers solved together on one GPU.
 
     ``variant`` 17 = the reference's 17-state / 6-input model; 12 = QUAD12 (states 0..11,
-    inputs 0..3, gimbal frozen).  ``blastThruster`` is stored but, exactly as in the
+    inputs 0..3, gimbal frozen); 13 = QUAT13 (QUAD12 with the attitude as a unit quaternion,
+    x = [p, q(w,x,y,z), v, omega], quaternion algebra of the reference's utils/MathUtils.py).  ``blastThruster`` is stored but, exactly as in the
     reference (blastermodel.py:43), never used: the blast thrust is parameter p[24].
     """
 
@@ -117,7 +118,9 @@ class BlasterMPC:
             raise MpcbError("BlasterMPC needs a CUDA device; this package has no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.nx, self.nu = (17, 6) if variant == 17 else (12, 4)
+        if variant not in (17, 12, 13):
+            raise ValueError("variant must be 17 (BLASTER17), 12 (QUAD12) or 13 (QUAT13)")
+        self.nx, self.nu = {17: (17, 6), 12: (12, 4), 13: (13, 4)}[int(variant)]
         self.ny, self.N, self.batch = self.nx + self.nu, int(N), int(batch)
         self.blastThruster, self.variant = float(blastThruster), int(variant)
         cfg = MpcbConfig()
@@ -153,6 +156,16 @@ class BlasterMPC:
                         1.22173, 0.523599, 1.5, 1.5, 2.5]])
         cb = np.array([[0, 0, 0, 0, -0.0872665, -0.0872665], [65, 65, 65, 65, 0.0872665, 0.0872665]], dtype=np.float64)
         J = np.diag([0.50781, 0.47314, 0.72975])
+        if variant == 13:
+            # QUAT13: Euler weights -> quaternion components; Euler boxes (10, 10, 20 deg) -> boxes on the vector
+            # part (sine of half the angle), q_w near 1; no gimbal, no POC states
+            hq = np.sin(np.array([0.174532925, 0.174532925, 0.349066]) / 2)
+            q = np.diag(Q)
+            Q = np.diag(np.concatenate([q[0:3], [1e3] * 4, q[6:12]]))
+            R = R[:4, :4]
+            sb = np.array([np.concatenate([sb[0, 0:3], [0.9], -hq, sb[0, 6:12]]),
+                           np.concatenate([sb[1, 0:3], [1.05], hq, sb[1, 6:12]])])
+            cb = cb[:, :4]
         sb = sb if statesBound is None else np.asarray(statesBound, dtype=np.float64)
         cb = cb if controlBound is None else np.asarray(controlBound, dtype=np.float64)
         return cls(9.0, J, 0.3434, 0.3475, N, N / 30.0, 0.03, Q, R, 10 * Q, 2.2 * 9.81, sb, cb, batch=batch,

@@ -39,7 +39,9 @@ class BlasterProblem:
 
     ``variant`` 17 = the reference's model (17 states / 6 inputs / 25 params),
     12 = QUAD12: states 0..11 and inputs 0..3 of the same model with the gimbal
-    frozen at alpha1 = alpha2 = 0.
+    frozen at alpha1 = alpha2 = 0 (SURVEY.md section 0 fact 2);
+    13 = QUAT13: QUAD12 with the attitude as a unit quaternion instead of Euler angles
+    (exists nowhere in the reference -- see ``f13``).
     """
 
     mass: float
@@ -67,7 +69,7 @@ class BlasterProblem:
 
     @property
     def nx(self):
-        return 17 if self.variant == 17 else 12
+        return {17: 17, 13: 13}.get(self.variant, 12)
 
     @property
     def nu(self):
@@ -93,6 +95,16 @@ def canonical_problem(N: int = 20, variant: int = 17) -> BlasterProblem:
                     0.0872665, 0.0872665, 0.0872665, 1.22173, 0.523599, 1.5, 1.5, 2.5])
     lbu = np.array([0, 0, 0, 0, -0.0872665, -0.0872665], dtype=np.float64)
     ubu = np.array([65, 65, 65, 65, 0.0872665, 0.0872665], dtype=np.float64)
+    if variant == 13:
+        # QUAT13: x = [p, q(w,x,y,z), v, omega].  Weights of the Euler angles go to the quaternion
+        # components; the Euler-angle boxes (10, 10, 20 deg) become boxes on the vector part
+        # (sin of half the angle) and q_w stays near 1.
+        Q13 = np.concatenate([Q[0:3], [1e3] * 4, Q[6:12]])
+        lb13 = np.concatenate([lbx[0:3], [0.9, -np.sin(0.174532925 / 2), -np.sin(0.174532925 / 2), -np.sin(0.349066 / 2)], lbx[6:12]])
+        ub13 = np.concatenate([ubx[0:3], [1.05, np.sin(0.174532925 / 2), np.sin(0.174532925 / 2), np.sin(0.349066 / 2)], ubx[6:12]])
+        return BlasterProblem(
+            mass=9.0, J=np.diag([0.50781, 0.47314, 0.72975]), l_x=0.3434, l_y=0.3475, c=0.03,
+            N=N, dt=2.0 / 60, Q=Q13, R=R[:4], Qt=10 * Q13, lbx=lb13, ubx=ub13, lbu=lbu[:4], ubu=ubu[:4], variant=13)
     nx, nu = (17, 6) if variant == 17 else (12, 4)
     return BlasterProblem(
         mass=9.0, J=np.diag([0.50781, 0.47314, 0.72975]), l_x=0.3434, l_y=0.3475, c=0.03,
@@ -234,6 +246,68 @@ def jac17(x, u, p, P: BlasterProblem):
     return fx, fu
 
 
+# --------------------------------------------------------------------------
+# QUAT13: the 12-state quadrotor with a quaternion attitude.
+# Not in the reference: its utils/MathUtils.py provides the quaternion algebra
+# (quatMultiplication :5-23, unitQuatInversion :25-39, quat2Rot :41-54) but no model uses
+# it.  PARITY UNPINNED for the model itself; it is tied to the Euler model by
+# construction (same forces and moments, R(q) = Rz Ry Rx at q = q(phi,theta,psi)) and
+# tested against it.  x = [p(3), q(w,x,y,z), v(3), omega(3)], u = [T0..T3].
+# --------------------------------------------------------------------------
+def quat_mul(a, b):
+    """MathUtils.quatMultiplication (Hamilton product, q = [w,x,y,z])."""
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                     a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1],
+                     a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def quat_to_rot(e):
+    """MathUtils.quat2Rot."""
+    w, x, y, z = e
+    return np.array([[2 * (w * w + x * x) - 1, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 2 * (w * w + y * y) - 1, 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 2 * (w * w + z * z) - 1]])
+
+
+def euler_to_quat(phi, th, psi):
+    """Quaternion of R = Rz(psi) Ry(theta) Rx(phi) (blastermodel.py:122)."""
+    cf, sf, ct, st, cp, sp = np.cos(phi / 2), np.sin(phi / 2), np.cos(th / 2), np.sin(th / 2), np.cos(psi / 2), np.sin(psi / 2)
+    return np.array([cp * ct * cf + sp * st * sf, cp * ct * sf - sp * st * cf, cp * st * cf + sp * ct * sf, sp * ct * cf - cp * st * sf])
+
+
+def x12_to_x13(x12):
+    """[p, euler, v, omega] -> [p, q, v, omega]."""
+    x12 = np.asarray(x12, dtype=np.float64)
+    return np.concatenate([x12[0:3], euler_to_quat(*x12[3:6]), x12[6:12]])
+
+
+def f13(x, u, p, P: BlasterProblem):
+    """pdot = v;  qdot = 1/2 q (x) [0, omega];  vdot = R(q) e3 (sum T + T_blast)/M + g  (the jet acts along
+    body z: gimbal frozen at 0, as in QUAD12);  omegadot as blastermodel.py:164."""
+    q, v, om, T = x[3:7], x[7:10], x[10:13], u[0:4]
+    qd = 0.5 * quat_mul(q, np.array([0.0, om[0], om[1], om[2]]))
+    vd = quat_to_rot(q)[:, 2] * (T.sum() + p[24]) / P.mass + np.array([0.0, 0.0, -GRAVITY])
+    omd = P.Jinv @ (_moment_map(P) @ T - np.cross(om, P.J @ om))
+    return np.concatenate([v, qd, vd, omd])
+
+
+def jac13(x, u, p, P: BlasterProblem):
+    """Analytic (df/dx, df/du) of ``f13``."""
+    (w, qx, qy, qz), om, T = x[3:7], x[10:13], u[0:4]
+    a, b, c = om
+    F = (T.sum() + p[24]) / P.mass
+    fx, fu = np.zeros((13, 13)), np.zeros((13, 4))
+    fx[0:3, 7:10] = np.eye(3)
+    fx[3:7, 3:7] = 0.5 * np.array([[0, -a, -b, -c], [a, 0, c, -b], [b, -c, 0, a], [c, b, -a, 0]])
+    fx[3:7, 10:13] = 0.5 * np.array([[-qx, -qy, -qz], [w, -qz, qy], [qz, w, -qx], [-qy, qx, w]])
+    fx[7:10, 3:7] = F * 2.0 * np.array([[qy, qz, w, qx], [-qx, -w, qz, qy], [2 * w, 0, 0, 2 * qz]])
+    fu[7:10, 0:4] = (quat_to_rot(x[3:7])[:, 2] / P.mass)[:, None]
+    fx[10:13, 10:13] = -P.Jinv @ (_skew(om) @ P.J - _skew(P.J @ om))
+    fu[10:13, 0:4] = P.Jinv @ _moment_map(P)
+    return fx, fu
+
+
 def _pad(x, u, P):
     if P.variant == 17:
         return x, u
@@ -245,11 +319,15 @@ def _pad(x, u, P):
 
 
 def f(x, u, p, P: BlasterProblem):
+    if P.variant == 13:
+        return f13(np.asarray(x, dtype=np.float64), np.asarray(u, dtype=np.float64), p, P)
     xx, uu = _pad(x, u, P)
     return f17(xx, uu, p, P)[:P.nx]
 
 
 def jac(x, u, p, P: BlasterProblem):
+    if P.variant == 13:
+        return jac13(np.asarray(x, dtype=np.float64), np.asarray(u, dtype=np.float64), p, P)
     xx, uu = _pad(x, u, P)
     fx, fu = jac17(xx, uu, p, P)
     return fx[:P.nx, :P.nx], fu[:P.nx, :P.nu]

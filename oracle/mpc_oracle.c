@@ -156,6 +156,85 @@ static void orc_jac17(const orc_problem *P, const double *x, const double *u, co
     }
 }
 
+/* QUAT13: the 12-state quadrotor with its attitude as a unit quaternion,
+ * x = [p(3), q(w,x,y,z), v(3), omega(3)], u = [T0..T3]; the quaternion algebra is that of the
+ * reference's utils/MathUtils.py (quatMultiplication :5-23, quat2Rot :41-54), which no model of
+ * the reference uses.  PARITY UNPINNED for the model; tested against the Euler model.
+ * Same padded signature as orc_f17 / orc_jac17 (the first 13 states / 4 inputs are used). */
+static void orc_f13(const orc_problem *P, const double *x, const double *u, const double *p, double *xd)
+{
+    const double w = x[3], qx = x[4], qy = x[5], qz = x[6];
+    const double *v = x + 7, *om = x + 10;
+    const double F = (u[0] + u[1] + u[2] + u[3] + p[24]) / P->mass;
+    for (int i = 0; i < 17; i++) xd[i] = 0.0;
+    for (int i = 0; i < 3; i++) xd[i] = v[i];
+    /* qdot = 1/2 q (x) [0, omega] */
+    xd[3] = 0.5 * (-qx * om[0] - qy * om[1] - qz * om[2]);
+    xd[4] = 0.5 * (w * om[0] + qy * om[2] - qz * om[1]);
+    xd[5] = 0.5 * (w * om[1] - qx * om[2] + qz * om[0]);
+    xd[6] = 0.5 * (w * om[2] + qx * om[1] - qy * om[0]);
+    /* vdot = R(q) e3 (sum T + T_blast)/M + g: third column of quat2Rot */
+    xd[7] = F * 2.0 * (qx * qz + w * qy);
+    xd[8] = F * 2.0 * (qy * qz - w * qx);
+    xd[9] = F * (2.0 * (w * w + qz * qz) - 1.0) - GRAV;
+    const double M[3] = {(u[1] + u[3] - u[0] - u[2]) * P->l_y, (-u[0] - u[3] + u[1] + u[2]) * P->l_x, (-u[0] - u[1] + u[2] + u[3]) * P->c};
+    double Jo[3], cr[3];
+    for (int i = 0; i < 3; i++) Jo[i] = P->J[3 * i] * om[0] + P->J[3 * i + 1] * om[1] + P->J[3 * i + 2] * om[2];
+    cr[0] = om[1] * Jo[2] - om[2] * Jo[1];
+    cr[1] = om[2] * Jo[0] - om[0] * Jo[2];
+    cr[2] = om[0] * Jo[1] - om[1] * Jo[0];
+    for (int i = 0; i < 3; i++)
+        xd[10 + i] = P->Jinv[3 * i] * (M[0] - cr[0]) + P->Jinv[3 * i + 1] * (M[1] - cr[1]) + P->Jinv[3 * i + 2] * (M[2] - cr[2]);
+}
+
+static void orc_jac13(const orc_problem *P, const double *x, const double *u, const double *p, double fx[17][17], double fu[17][6])
+{
+    const double w = x[3], qx = x[4], qy = x[5], qz = x[6];
+    const double *om = x + 10;
+    const double a = om[0], b = om[1], c = om[2];
+    const double m = 1.0 / P->mass, F = (u[0] + u[1] + u[2] + u[3] + p[24]) * m;
+    memset(fx, 0, sizeof(double) * 17 * 17);
+    memset(fu, 0, sizeof(double) * 17 * 6);
+    for (int i = 0; i < 3; i++) fx[i][7 + i] = 1.0;
+    const double Om[4][4] = {{0, -a, -b, -c}, {a, 0, c, -b}, {b, -c, 0, a}, {c, b, -a, 0}};
+    const double Xi[4][3] = {{-qx, -qy, -qz}, {w, -qz, qy}, {qz, w, -qx}, {-qy, qx, w}};
+    for (int i = 0; i < 4; i++) {
+        for (int j = 0; j < 4; j++) fx[3 + i][3 + j] = 0.5 * Om[i][j];
+        for (int j = 0; j < 3; j++) fx[3 + i][10 + j] = 0.5 * Xi[i][j];
+    }
+    const double dr3[3][4] = {{qy, qz, w, qx}, {-qx, -w, qz, qy}, {2 * w, 0, 0, 2 * qz}};
+    const double r3[3] = {2.0 * (qx * qz + w * qy), 2.0 * (qy * qz - w * qx), 2.0 * (w * w + qz * qz) - 1.0};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 4; j++) fx[7 + i][3 + j] = 2.0 * F * dr3[i][j];
+        for (int j = 0; j < 4; j++) fu[7 + i][j] = m * r3[i];
+    }
+    double Jo[3], D[3][3];
+    for (int i = 0; i < 3; i++) Jo[i] = P->J[3 * i] * om[0] + P->J[3 * i + 1] * om[1] + P->J[3 * i + 2] * om[2];
+    const double So[3][3] = {{0, -om[2], om[1]}, {om[2], 0, -om[0]}, {-om[1], om[0], 0}};
+    const double SJ[3][3] = {{0, -Jo[2], Jo[1]}, {Jo[2], 0, -Jo[0]}, {-Jo[1], Jo[0], 0}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = -SJ[i][j];
+            for (int k = 0; k < 3; k++) s += So[i][k] * P->J[3 * k + j];
+            D[i][j] = s;
+        }
+    const double G[3][4] = {{-P->l_y, P->l_y, -P->l_y, P->l_y}, {-P->l_x, P->l_x, P->l_x, -P->l_x}, {-P->c, -P->c, P->c, P->c}};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += P->Jinv[3 * i + k] * D[k][j];
+            fx[10 + i][10 + j] = -s;
+        }
+        for (int j = 0; j < 4; j++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += P->Jinv[3 * i + k] * G[k][j];
+            fu[10 + i][j] = s;
+        }
+    }
+}
+
+#define MODEL_F orc_f17
+#define MODEL_JAC orc_jac17
 #define NX 17
 #define NU 6
 #define SFX(n) b17_##n
@@ -171,26 +250,46 @@ static void orc_jac17(const orc_problem *P, const double *x, const double *u, co
 #undef NX
 #undef NU
 #undef SFX
+#undef MODEL_F
+#undef MODEL_JAC
+
+#define MODEL_F orc_f13
+#define MODEL_JAC orc_jac13
+#define NX 13
+#define NU 4
+#define SFX(n) q13_##n
+#include "mpc_oracle_body.h"
+#undef NX
+#undef NU
+#undef SFX
+#undef MODEL_F
+#undef MODEL_JAC
+
+#define ORC_NX(P) ((P)->variant == 17 ? 17 : (P)->variant == 13 ? 13 : 12)
+#define ORC_NU(P) ((P)->variant == 17 ? 6 : 4)
 
 /* ------------------------------------------------------------------ exported API */
 void orc_f(const orc_problem *P, const double *x, const double *u, const double *p, double *xd)
 {
-    if (P->variant == 17) b17_f(P, x, u, p, xd); else q12_f(P, x, u, p, xd);
+    if (P->variant == 17) b17_f(P, x, u, p, xd); else if (P->variant == 13) q13_f(P, x, u, p, xd); else q12_f(P, x, u, p, xd);
 }
 
 void orc_rk4_sens(const orc_problem *P, const double *x, const double *u, const double *p, double *xn, double *BAt)
 {
-    if (P->variant == 17) b17_rk4_sens(P, x, u, p, xn, BAt); else q12_rk4_sens(P, x, u, p, xn, BAt);
+    if (P->variant == 17) b17_rk4_sens(P, x, u, p, xn, BAt);
+    else if (P->variant == 13) q13_rk4_sens(P, x, u, p, xn, BAt);
+    else q12_rk4_sens(P, x, u, p, xn, BAt);
 }
 
 void orc_plant_step_batch(const orc_problem *P, const double *x, const double *u, const double *p, int p_per_inst,
                           double *xn, int B, int nthreads)
 {
-    const int nx = P->variant == 17 ? 17 : 12, nu = P->variant == 17 ? 6 : 4;
+    const int nx = ORC_NX(P), nu = ORC_NU(P);
 #pragma omp parallel for num_threads(nthreads) schedule(static)
     for (int i = 0; i < B; i++) {
         const double *pi = p + (p_per_inst ? (size_t)i * 25 : 0);
         if (P->variant == 17) b17_plant_step(P, x + (size_t)i * nx, u + (size_t)i * nu, pi, xn + (size_t)i * nx);
+        else if (P->variant == 13) q13_plant_step(P, x + (size_t)i * nx, u + (size_t)i * nu, pi, xn + (size_t)i * nx);
         else q12_plant_step(P, x + (size_t)i * nx, u + (size_t)i * nu, pi, xn + (size_t)i * nx);
     }
 }
@@ -203,8 +302,8 @@ void orc_plant_step_batch(const orc_problem *P, const double *x, const double *u
 int orc_rti_solve_batch(const orc_problem *P, double *X, double *U, const double *x0, const double *yref, int yref_mode,
                         const double *p, int p_mode, int32_t *status, int32_t *iters, int B, int nthreads)
 {
-    const int nx = P->variant == 17 ? 17 : 12, nu = P->variant == 17 ? 6 : 4, ny = nx + nu, N = P->N;
-    const size_t wsz = P->variant == 17 ? b17_ws_doubles(N) : q12_ws_doubles(N);
+    const int nx = ORC_NX(P), nu = ORC_NU(P), ny = nx + nu, N = P->N;
+    const size_t wsz = P->variant == 17 ? b17_ws_doubles(N) : P->variant == 13 ? q13_ws_doubles(N) : q12_ws_doubles(N);
     int fail = 0;
     if (nthreads < 1) nthreads = 1;
 #pragma omp parallel num_threads(nthreads)
@@ -222,6 +321,9 @@ int orc_rti_solve_batch(const orc_problem *P, double *X, double *U, const double
             int it = 0, st;
             if (P->variant == 17)
                 st = b17_rti_solve(P, X + (size_t)i * (N + 1) * nx, U + (size_t)i * N * nu, x0 + (size_t)i * nx, yr, yref_mode == 2,
+                                   pp, p_mode == 2, ws, &it);
+            else if (P->variant == 13)
+                st = q13_rti_solve(P, X + (size_t)i * (N + 1) * nx, U + (size_t)i * N * nu, x0 + (size_t)i * nx, yr, yref_mode == 2,
                                    pp, p_mode == 2, ws, &it);
             else
                 st = q12_rti_solve(P, X + (size_t)i * (N + 1) * nx, U + (size_t)i * N * nu, x0 + (size_t)i * nx, yr, yref_mode == 2,

@@ -1,6 +1,7 @@
 /* Body of the C oracle, included once per model variant with
  *   NX, NU   compile-time state/input dimension
  *   SFX(x)   name-mangling macro
+ *   MODEL_F, MODEL_JAC   the dynamics and its Jacobians (arrays padded to 17 states / 6 inputs)
  * TEST INFRASTRUCTURE ONLY -- see mpc_oracle.c for the header comment.
  *
  * Stage variable ordering everywhere: z_k = [du_k (NU); dx_k (NX)], NZ = NU+NX.
@@ -60,7 +61,7 @@ static void SFX(f)(const orc_problem *P, const double *x, const double *u, const
     double x17[17] = {0}, u6[6] = {0}, out[17];
     for (int i = 0; i < NX; i++) x17[i] = x[i];
     for (int i = 0; i < NU; i++) u6[i] = u[i];
-    orc_f17(P, x17, u6, p, out);
+    MODEL_F(P, x17, u6, p, out);
     for (int i = 0; i < NX; i++) xd[i] = out[i];
 }
 
@@ -85,8 +86,8 @@ static void SFX(rk4_sens)(const orc_problem *P, const double *x, const double *u
         for (int c = 0; c < NZ; c++)
             for (int i = 0; i < NX; i++) Ss[c][i] = St[c][i] + ca[s] * h * K[c][i];
         for (int i = 0; i < NX; i++) x17[i] = xs[i];
-        orc_f17(P, x17, u6, p, f17);
-        orc_jac17(P, x17, u6, p, fx, fu);
+        MODEL_F(P, x17, u6, p, f17);
+        MODEL_JAC(P, x17, u6, p, fx, fu);
         for (int i = 0; i < NX; i++) k[i] = f17[i];
         for (int c = 0; c < NZ; c++)
             for (int i = 0; i < NX; i++) {

@@ -59,6 +59,9 @@ int emu_rti_solve(const Params *P, double *X, double *U, const double *x0, const
     if (P->variant == 17)
         return one ? rti_one<17, 6, 1>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out)
                    : rti_one<17, 6, 2>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+    if (P->variant == 13)
+        return one ? rti_one<13, 4, 1>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out)
+                   : rti_one<13, 4, 2>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
     return one ? rti_one<12, 4, 1>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out)
                : rti_one<12, 4, 2>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
 }
@@ -66,6 +69,7 @@ int emu_rti_solve(const Params *P, double *X, double *U, const double *x0, const
 void emu_plant_step(const Params *P, const double *x, const double *u, const double *p, double *xn)
 {
     if (P->variant == 17) plant_step_thread<17, 6, double>(*P, x, u, p, xn);
+    else if (P->variant == 13) plant_step_thread<13, 4, double>(*P, x, u, p, xn);
     else plant_step_thread<12, 4, double>(*P, x, u, p, xn);
 }
 }
@@ -123,5 +127,6 @@ extern "C" void emu_rti_solve4(const Params *P, int nb, double *X, double *U, co
                                int *status, int *iters)
 {
     if (P->variant == 17) rti_four<17, 6>(*P, nb, X, U, x0, yref, p, status, iters);
+    else if (P->variant == 13) rti_four<13, 4>(*P, nb, X, U, x0, yref, p, status, iters);
     else rti_four<12, 4>(*P, nb, X, U, x0, yref, p, status, iters);
 }

@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -34,7 +35,10 @@ def test_config_default_is_the_reference_constants_and_struct_layouts_agree():
     assert abs(cfg.dt - 1 / 30) < 1e-16 and cfg.mass == 9.0 and cfg.J[4] == 0.47314
     assert list(cfg.R) == [5e-2] * 4 + [1e-5] * 2 and cfg.Qt[0] == 1e4 and cfg.ubu[0] == 65 and cfg.lbx[2] == 0
     assert (cfg.tol_stat, cfg.tol_eq, cfg.tol_ineq, cfg.tol_comp) == (1e-6, 1e-8, 1e-8, 1e-8)
-    assert lib.mpcb_config_default(C.byref(cfg), 13, 20) != 0  # unknown variant
+    assert lib.mpcb_config_default(C.byref(cfg), 13, 20) == 0  # QUAT13: weights / boxes of the quaternion components at 3..6
+    assert cfg.variant == 13 and list(cfg.Q)[:13] == [1e3] * 7 + [5.0] * 3 + [10.0] * 3 and list(cfg.Q)[13:] == [0.0] * 4
+    assert (cfg.lbx[3], cfg.ubx[3]) == (0.9, 1.05) and abs(cfg.ubx[6] - np.sin(0.349066 / 2)) < 1e-15 and cfg.ubx[7] == 1.0
+    assert lib.mpcb_config_default(C.byref(cfg), 14, 20) != 0  # unknown variant
 
 
 def test_no_cpu_fallback():

@@ -696,3 +696,42 @@ def test_full_size_config5_sample_against_oracle(cuda_device, variant):
     assert np.abs(u0[ti].cpu().numpy()[ok] - uo[ok]).max() < TOL
     del mpc
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B,qp8", [(96, False), (200, True)])
+def test_quat13_variant_matches_oracle(cuda_device, B, qp8, monkeypatch):
+    """QUAT13: the 12-state quadrotor with its attitude as a unit quaternion, dynamics
+    built on the quaternion algebra of the reference's utils/MathUtils.py.  No reference model uses it,
+    so the checks are: linearisation, two closed-loop solves and the plant step against the oracles
+    (whose QUAT13 model is itself tested against the Euler model: tests/test_oracle.py), on both QP kernels."""
+    N = 12
+    P = bo.canonical_problem(N, 13)
+    x0, yref = sc.random_setpoints(B, seed=91, nx=13, nu=4)
+    trim = sc.hover_trim(4)
+    if qp8:
+        monkeypatch.setenv("MPCB_QP8_BATCH", "1")
+        monkeypatch.setenv("MPCB_QP8_WARPS", "9")
+    mpc = _mpc(N, B, 13)
+    orc = co.BatchRTI(P, B)
+    mpc.reset(x0, trim)
+    orc.reset(x0, trim)
+    Ag, Bg, bg = mpc.linearize()
+    for i in (0, B - 1):
+        for k in (0, N - 1):
+            xn, A, Bm = co.rk4_sens(P, x0[i], trim, bo.default_params())
+            assert np.abs(Ag[i, k].cpu().numpy() - A).max() < 1e-13 and np.abs(Bg[i, k].cpu().numpy() - Bm).max() < 1e-13
+            assert np.abs(bg[i, k].cpu().numpy() - (xn - x0[i])).max() < 1e-13
+    x = x0
+    for step in range(2):
+        u0, X, U, st = mpc.solve(x, yref)
+        uo, Xo, Uo, sto = orc.solve(x, yref)
+        assert (st.cpu().numpy() == sto).all() and (mpc.iters.cpu().numpy() == orc.iters).all()
+        ok = sto == 0
+        assert ok.mean() > 0.9
+        assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+        xn = mpc.step_plant(torch.as_tensor(x, device="cuda"), torch.as_tensor(uo, device="cuda")).cpu().numpy()
+        x = co.plant_step(P, x, uo)
+        assert np.abs(xn - x).max() < 1e-12
+        assert np.abs(np.linalg.norm(x[:, 3:7], axis=1) - 1).max() < 1e-6      # RK4 keeps |q| = 1 to O(dt^5)
+    with pytest.raises(Exception):
+        mpc.command_map(torch.as_tensor(x, device="cuda"), torch.as_tensor(uo, device="cuda"))

@@ -15,7 +15,7 @@ from oracle import c_oracle as co
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("variant", [17, 12])
+@pytest.mark.parametrize("variant", [17, 12, 13])
 def test_emulated_kernels_match_oracle(variant):
     P = bo.canonical_problem(10, variant)
     x0, yref = sc.random_setpoints(2, seed=31, nx=P.nx, nu=P.nu)
@@ -24,7 +24,7 @@ def test_emulated_kernels_match_oracle(variant):
         c = co.BatchRTI(P, 1, nthreads=1)
         X = np.zeros((P.N + 1, P.nx))
         U = np.zeros((P.N, P.nu))
-        if i == 1:  # second instance starts from an initialised iterate
+        if i == 1 or variant == 13:  # initialised iterate (always for QUAT13: the all-zero iterate is no quaternion)
             X[:] = x0[i]
             U[:] = sc.hover_trim(P.nu)
             c.reset(x0[i:i + 1], sc.hover_trim(P.nu))
@@ -112,7 +112,7 @@ def test_emulated_poc_generator_matches_oracle_and_reference_golden():
         assert np.abs(Jm_a - Jm).max() < 2e-3 and np.abs(Je_a - Je).max() < 2e-3 and np.abs(Jp_a - Jp).max() < 2e-3
 
 
-@pytest.mark.parametrize("variant,N,nb", [(17, 10, 4), (12, 10, 4), (17, 6, 3), (12, 5, 1), (12, 8, 11), (17, 5, 9)])
+@pytest.mark.parametrize("variant,N,nb", [(17, 10, 4), (12, 10, 4), (17, 6, 3), (12, 5, 1), (12, 8, 11), (17, 5, 9), (13, 8, 6)])
 def test_emulated_four_instances_per_warp_kernel_matches_oracle(variant, N, nb):
     """mpcb_qp8.cuh (four instances per warp, eight lanes each) compiled for the host: full and
     partly filled warps, two RTI steps (the four instances then differ in their IPM iteration

@@ -255,3 +255,47 @@ def test_poc_oracle_reproduces_the_reference_jacobian_poc_solver():
     # the ndarray call pattern of the reference accumulates the position perturbations (documented, not a target)
     acc = np.cumsum(g["J_pos"][0], axis=1)
     assert np.abs(acc - g["J_pos_ndarray_call"]).max() < 1e-3
+
+
+def test_quat13_model_is_the_euler_model_in_quaternion_coordinates():
+    """QUAT13 exists nowhere in the reference, so it is pinned to what does: at
+    q = q(phi, theta, psi) its rotation matrix is the OCP's Rz Ry Rx (blastermodel.py:122) through
+    MathUtils.quat2Rot, its translational and angular accelerations equal QUAD12's, its qdot is the
+    Euler-rate field pushed through dq/d(euler); Jacobians against central differences; the C oracle
+    against the NumPy one; |q| is an invariant of the continuous dynamics."""
+    P13, P12 = bo.canonical_problem(6, 13), bo.canonical_problem(6, 12)
+    rng = np.random.default_rng(0)
+    p = bo.default_params()
+    eps = 1e-6
+    for _ in range(6):
+        x12 = np.concatenate([rng.uniform(-1, 1, 3), rng.uniform(-0.3, 0.3, 3), rng.uniform(-1, 1, 3), rng.uniform(-0.2, 0.2, 3)])
+        u = rng.uniform(5, 40, 4)
+        x13 = bo.x12_to_x13(x12)
+        assert abs(np.linalg.norm(x13[3:7]) - 1) < 1e-14
+        assert np.abs(bo.quat_to_rot(x13[3:7]) - bo._rot(*x12[3:6])).max() < 1e-14
+        f12, f13 = bo.f(x12, u, p, P12), bo.f(x13, u, p, P13)
+        assert np.abs(f12[0:3] - f13[0:3]).max() < 1e-14 and np.abs(f12[6:12] - f13[7:13]).max() < 1e-12
+        Jq = np.stack([(bo.euler_to_quat(*(x12[3:6] + eps * np.eye(3)[i])) - bo.euler_to_quat(*(x12[3:6] - eps * np.eye(3)[i]))) / (2 * eps)
+                       for i in range(3)], axis=1)
+        assert np.abs(Jq @ f12[3:6] - f13[3:7]).max() < 1e-8
+        assert abs(x13[3:7] @ f13[3:7]) < 1e-15                               # d|q|^2/dt = 0
+        fx, fu = bo.jac(x13, u, p, P13)
+        fxn = np.stack([(bo.f(x13 + eps * np.eye(13)[i], u, p, P13) - bo.f(x13 - eps * np.eye(13)[i], u, p, P13)) / (2 * eps) for i in range(13)], axis=1)
+        fun = np.stack([(bo.f(x13, u + eps * np.eye(4)[i], p, P13) - bo.f(x13, u - eps * np.eye(4)[i], p, P13)) / (2 * eps) for i in range(4)], axis=1)
+        assert np.abs(fx - fxn).max() < 1e-7 and np.abs(fu - fun).max() < 1e-8
+        assert np.abs(co.f(P13, x13, u, p) - f13).max() < 1e-13
+        xn, A, B = co.rk4_sens(P13, x13, u, p)
+        xn2, A2, B2 = bo.rk4_sens(x13, u, p, P13)
+        assert np.abs(xn - xn2).max() < 1e-13 and np.abs(A - A2).max() < 1e-13 and np.abs(B - B2).max() < 1e-13
+    # one RTI iteration: dense-KKT NumPy oracle against the Riccati C oracle
+    x0, yref = sc.random_setpoints(4, seed=17, nx=13, nu=4)
+    trim = sc.hover_trim(4)
+    c = co.BatchRTI(P13, 4, nthreads=1)
+    c.reset(x0, trim)
+    u0, X, U, st = c.solve(x0, yref)
+    for i in range(4):
+        o = bo.RTIOracle(P13)
+        o.reset(x0[i], trim)
+        uo, Xo, Uo, so = o.solve(x0[i], yref[i])
+        assert so == st[i] == 0
+        assert np.abs(Uo - U[i]).max() < 1e-7 and np.abs(Xo - X[i]).max() < 1e-8

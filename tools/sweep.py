@@ -15,7 +15,7 @@ from mpc_blaster_b200 import BlasterMPC, scenarios as sc  # noqa: E402
 
 
 def run(B, N, variant, scen, steps=5, warmup=2, ws_batch=0):
-    nx, nu = (17, 6) if variant == 17 else (12, 4)
+    nx, nu = {17: (17, 6), 12: (12, 4), 13: (13, 4)}[variant]
     mpc = BlasterMPC.canonical(N=N, batch=B, variant=variant, ws_batch=ws_batch)
     if scen == "track":
         x0, yref = sc.lemniscate_tracking(B, N, nx=nx, nu=nu)
