@@ -164,6 +164,88 @@ __global__ void bench_kernel(const double *W0, const double *H0, double *Lall, l
     if (acc == 1.2345) Lall[0] = acc;
 }
 
+// V9: two warps per instance, the 17 columns of W split 9 + 8 between them; partial dot products and partial
+// |w_j|^2 exchanged through shared memory with one 64-thread barrier per pivot (double-buffered by pivot parity).
+struct Sm2 {
+    alignas(32) double vrow[2][2][12];   // [warp][parity][own columns]
+    double part[2][2][32];               // [parity][warp][lane]  partial dots
+    double pn[2][2];                     // [parity][warp]        partial |w_j|^2
+    double hd[24], ds[24];
+    double Lout[NZ * 24];
+};
+template <int NC>
+__device__ __forceinline__ void pivots_2w(Sm2 &sm, double (&w)[NC], int warp, int lane)
+{
+    const sptr lrow = sptr_of(sm.Lout + (lane < NZ ? lane : 0) * 24);
+#pragma unroll 1
+    for (int j = 0; j < NZ; j++) {
+        const int par = j & 1;
+        const sptr vr = sptr_of(sm.vrow[warp][par]);
+        const bool piv = (lane == j);
+        double v[NC];
+        sp_row_store<0, NC>(vr, w, piv);
+        warp_sync();
+        sp_row_load<0, NC>(vr, v);
+        double d0 = 0, d1 = 0, e0 = 0, e1 = 0;
+#pragma unroll
+        for (int c = 0; c + 1 < NC; c += 2) { d0 += v[c] * w[c]; d1 += v[c + 1] * w[c + 1]; e0 += v[c] * v[c]; e1 += v[c + 1] * v[c + 1]; }
+        if (NC & 1) { d0 += v[NC - 1] * w[NC - 1]; e0 += v[NC - 1] * v[NC - 1]; }
+        sm.part[par][warp][lane] = d0 + d1;
+        if (lane == 0) sm.pn[par][warp] = e0 + e1;
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        const double dot = sm.part[par][0][lane] + sm.part[par][1][lane];
+        const double djj = sm.pn[par][0] + sm.pn[par][1];
+        const double hdj = sm.hd[j], dsj = sm.ds[j];
+        const double s2v = hdj + djj;
+        const double rs = fast_rsqrt(s2v);
+        const double idjj = fast_rcp(djj);
+        const double sig = s2v * rs;
+        const double kap = (djj > 0) ? (sig - dsj) * idjj : 0.0;
+        const double lij = (lane > j) ? dot * rs : 0.0;
+        const double f = lij * kap;
+#pragma unroll
+        for (int c = 0; c < NC; c++) w[c] -= f * v[c];
+        if (warp == 0) sp_st1<0>(sptr_add(lrow, j), piv ? sig : lij, lane < NZ && lane >= j);
+    }
+}
+__global__ void __launch_bounds__(64) bench_kernel2w(const double *W0, const double *H0, double *Lall, long long *cyc, int rounds)
+{
+    __shared__ Sm2 s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int inst = blockIdx.x;
+    constexpr int NC0 = 9, NC1 = 8;
+    double w0[NC0];
+    for (int c = 0; c < NC0; c++) {
+        const int col = warp == 0 ? c : NC0 + c;
+        w0[c] = (lane < NZ && col < NX) ? W0[((size_t)(inst % 64) * NZ + lane) * NX + col] : 0.0;
+    }
+    if (warp == 0 && lane < NZ) { s.hd[lane] = H0[(inst % 64) * NZ + lane]; s.ds[lane] = sqrt(s.hd[lane]); }
+    __syncthreads();
+    double acc = 0;
+    long long t0 = clock64();
+    for (int r = 0; r < rounds; r++) {
+        if (warp == 0) {
+            double w[NC0];
+#pragma unroll
+            for (int c = 0; c < NC0; c++) w[c] = w0[c] + acc * 1e-300;
+            pivots_2w<NC0>(s, w, 0, lane);
+            acc += w[0];
+        } else {
+            double w[NC1];
+#pragma unroll
+            for (int c = 0; c < NC1; c++) w[c] = w0[c] + acc * 1e-300;
+            pivots_2w<NC1>(s, w, 1, lane);
+            acc += w[0];
+        }
+        __syncthreads();
+    }
+    long long t1 = clock64();
+    if (warp == 0 && lane < NZ)
+        for (int j = 0; j < NZ; j++) Lall[((size_t)inst * NZ + lane) * NZ + j] = (j <= lane) ? s.Lout[lane * 24 + j] : 0.0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+    if (acc == 1.2345) Lall[0] = acc;
+}
+
 int main()
 {
     const int NI = 64;
@@ -202,6 +284,14 @@ int main()
             for (size_t i = 0; i < L0.size(); i++) md = fmax(md, fabs(L0[i] - L1[i]));
             printf("warps/SM %2d  variant %d: %7.1f cycles per pivot   max|L - L_v0| = %.2e\n", bps, v, (double)hc / rounds / NZ, md);
         }
+    }
+    for (int bps : {1, 7, 14}) {
+        for (int rep = 0; rep < 2; rep++) { bench_kernel2w<<<148 * bps, 64>>>(dW, dH, dL, dc, rounds); cudaDeviceSynchronize(); }
+        cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(L1.data(), dL, L0.size() * 8, cudaMemcpyDeviceToHost);
+        double md = 0;
+        for (size_t i = 0; i < L0.size(); i++) md = fmax(md, fabs(L0[i] - L1[i]));
+        printf("instances/SM %2d  two warps per instance (columns 9+8): %7.1f cycles per pivot   max|L - L_v0| = %.2e\n", bps, (double)hc / rounds / NZ, md);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
