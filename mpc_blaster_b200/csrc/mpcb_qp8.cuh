@@ -26,14 +26,27 @@ struct Qp8Group {
     alignas(16) double rec[L::O_Z];  // head of a stage record: [BAt | Lu | invd | lvec | rb]
     double lxx[L::LXX];              // factor of P_{k+1} / P_k, row-major, zero upper triangle
     double vrow[2][L::NXP];          // pivot row broadcast (double buffered)
-    double vz[L::NZP];               // a stage vector every lane of the group reads (z_k or dz_k)
-    double hd[L::NZP], ds[L::NZP];   // Hd_k and sqrt(Hd_k) of every row (pivot loop)
-    double cPi[L::NXP], cZx[L::NXP], cPv[L::NXP], cDx[L::NXP], sT1[L::NXP], sT2[L::NXP], sRb[L::NXP];
+    // Three pairs of arrays are never live at the same time and share storage (19.1 -> 18.1 KB per QUAD12 warp:
+    // 12 instead of 11 warps per SM; 22.5 -> 20.9 KB and 9 -> 10 warps for QUAT13):
+    union {
+        double vz[L::NZP];           // a stage vector every lane of the group reads (z_k or dz_k): dead once r_k and the carry are formed
+        double hd[L::NZP];           // Hd_k of every row, written after the W product for the pivot loop
+    };
+    double ds[L::NZP];               // sqrt(Hd_k) of every row (pivot loop)
+    union {
+        double cPi[L::NXP];          // backward sweep S1: pi_{k+1}
+        double cDx[L::NXP];          // forward sweeps: dx_k (zeroed at their start)
+    };
+    union {
+        double sRb[L::NXP];          // r_k (S1) / dx_{k+1} (S4): last read when sT1 is formed ...
+        double sT2[L::NXP];          // ... before t2 = P r + p is written (a sync lies between)
+    };
+    double cZx[L::NXP], cPv[L::NXP], sT1[L::NXP];  // carried: dx-part of z_{k+1}, p_{k+1}; temporary L' r
     // Pad so that consecutive groups are 32 bytes (mod 128) apart: the four groups of a warp then hit
     // distinct banks when each broadcasts one word to its lanes, and a 64-byte run per group splits into
     // the minimal two wavefronts.  (QUAD12's unpadded group is a multiple of 128 bytes: every broadcast
     // was a 4-way bank conflict, 43 % of all shared-memory wavefronts in ncu.)
-    static constexpr int kBody = L::O_Z + L::LXX + 2 * L::NXP + 3 * L::NZP + 7 * L::NXP;
+    static constexpr int kBody = L::O_Z + L::LXX + 2 * L::NXP + 2 * L::NZP + 5 * L::NXP;
     double pad[(4 - kBody % 16 + 16) % 16 == 0 ? 16 : (4 - kBody % 16 + 16) % 16];
 };
 static_assert(sizeof(Qp8Group<17, 6>) % 128 == 32 && sizeof(Qp8Group<12, 4>) % 128 == 32 && sizeof(Qp8Group<13, 4>) % 128 == 32,
