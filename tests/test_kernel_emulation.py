@@ -132,3 +132,23 @@ def test_emulated_four_instances_per_warp_kernel_matches_oracle(variant, N, nb):
         assert (st == stc).all() and (st == 0).all() and (it == c.iters).all()
         assert np.abs(Xc - X).max() < 1e-8 and np.abs(Uc - U).max() < 1e-7
         x = co.plant_step(P, x, u0)
+
+
+def test_emulated_kernel_reference_script_configuration():
+    """The configuration simulation_blaster.py runs (N = 60, Tf = 2.0, parameters from the POC-Jacobian
+    generator's reference mode, x0 = 0, set-point of :47-48, zero initial iterate) through the kernel
+    source on the host: two control steps against the C oracle."""
+    from oracle import poc_oracle as po
+    P = bo.canonical_problem(60)
+    _, J_mot, J_eul, J_pos = po.solve_jacobians([0, 0, 0], [0, 0], [0, 0, 4])
+    p = bo.pack_params(J_mot, J_eul, J_pos, 2.2 * 9.81)
+    x0, yref = bo.canonical_x0_yref()
+    X, U = np.zeros((61, 17)), np.zeros((60, 6))
+    c = co.BatchRTI(P, 1, nthreads=1)
+    x = x0.copy()
+    for step in range(2):
+        st, it, _, _ = eb.rti_solve(P, X, U, x, yref, p)
+        u0, Xc, Uc, stc = c.solve(x[None], yref, p)
+        assert st == stc[0] == 0 and it == c.iters[0]
+        assert np.abs(Xc[0] - X).max() < 1e-8 and np.abs(Uc[0] - U).max() < 1e-7
+        x = co.plant_step(P, x, u0[0], p)[0]
