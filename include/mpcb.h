@@ -76,6 +76,9 @@ typedef struct mpcb_handle mpcb_handle;
 /* canonical constants of reference simulation_blaster.py:12-30, dt = 1/30 s */
 int mpcb_config_default(mpcb_config *cfg, int variant, int N);
 
+/* Fails (message through mpcb_last_error(NULL)) without a CUDA device, for dtype != MPCB_F64, for boxes without an
+ * interior (lbx < ubx and lbu < ubu must hold strictly: pin a variable with a tiny box, not a zero-width one), for
+ * negative Q / Qt or non-positive R entries. */
 int mpcb_create(const mpcb_config *cfg, mpcb_handle **out);
 int mpcb_destroy(mpcb_handle *h);
 const char *mpcb_last_error(const mpcb_handle *h); /* h may be NULL: error of the last failed create */

@@ -440,6 +440,19 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         return fail(nullptr, "only dtype = MPCB_F64 is implemented (an interior point with active state bounds is not viable in FP32, DESIGN.md)");
     if (cfg->max_batch < 1) return fail(nullptr, "max_batch must be >= 1");
     if (!(cfg->dt > 0) || !(cfg->mass > 0)) return fail(nullptr, "dt and mass must be positive");
+    {
+        // an interior point needs boxes with an interior: lb < ub strictly (a zero-width box would start with a zero
+        // slack and an infinite multiplier -> NaN status on every instance).  Pin a variable with a tiny box instead.
+        const int nxv = cfg->variant == 17 ? 17 : cfg->variant == 13 ? 13 : 12, nuv = cfg->variant == 17 ? 6 : 4;
+        for (int i = 0; i < nxv; i++)
+            if (!(cfg->lbx[i] < cfg->ubx[i])) return fail(nullptr, "state bounds must satisfy lbx < ubx strictly (zero-width or inverted box)");
+        for (int i = 0; i < nuv; i++)
+            if (!(cfg->lbu[i] < cfg->ubu[i])) return fail(nullptr, "input bounds must satisfy lbu < ubu strictly (zero-width or inverted box)");
+        for (int i = 0; i < nxv; i++)
+            if (!(cfg->Q[i] >= 0) || !(cfg->Qt[i] >= 0)) return fail(nullptr, "weights must be non-negative");
+        for (int i = 0; i < nuv; i++)
+            if (!(cfg->R[i] > 0)) return fail(nullptr, "input weights R must be positive (strict convexity of the QP)");
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail(nullptr, "no CUDA device: this library has no CPU path", e);

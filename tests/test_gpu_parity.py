@@ -363,6 +363,17 @@ def test_api_misuse_is_reported_not_crashed(cuda_device):
         mpc.solve(x0[:4, :5], yref[:4])
     u0, X, U, st = mpc.solve(x0[:4], yref[:4])  # still usable afterwards
     assert int((st == 0).sum()) == 4
+    # boxes without an interior and non-convex weights are refused at construction, not reported as NaN statuses later
+    from mpc_blaster_b200 import BlasterMPC
+    P = bo.canonical_problem(5)
+    cb = np.array([P.lbu, P.ubu])
+    cb[:, 4] = 0.0
+    with pytest.raises(MpcbError, match="lbu < ubu"):
+        BlasterMPC.canonical(N=5, batch=2, controlBound=cb)
+    sb = np.array([P.lbx, P.ubx])
+    sb[0, 8], sb[1, 8] = 1.0, -1.0
+    with pytest.raises(MpcbError, match="lbx < ubx"):
+        BlasterMPC.canonical(N=5, batch=2, statesBound=sb)
 
 
 def test_million_instance_chunking_smoke(cuda_device, monkeypatch):
