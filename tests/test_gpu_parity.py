@@ -746,3 +746,36 @@ def test_quat13_variant_matches_oracle(cuda_device, B, qp8, monkeypatch):
         assert np.abs(np.linalg.norm(x[:, 3:7], axis=1) - 1).max() < 1e-6      # RK4 keeps |q| = 1 to O(dt^5)
     with pytest.raises(Exception):
         mpc.command_map(torch.as_tensor(x, device="cuda"), torch.as_tensor(uo, device="cuda"))
+
+
+@pytest.mark.parametrize("qp8", [False, True])
+def test_nan_and_inf_inputs_are_reported_per_instance(cuda_device, qp8, monkeypatch):
+    """A NaN in one instance's x0, an infinite set-point in another's and an x0 a kilometre outside the arena
+    in a third: statuses 1 / 1 / 3 (NaN, NaN, min-step) as the C oracle reports them, their iterates untouched,
+    every other instance of the warp / batch solved to the usual parity."""
+    N, B = 10, 37
+    if qp8:
+        monkeypatch.setenv("MPCB_QP8_BATCH", "1")
+        monkeypatch.setenv("MPCB_QP8_WARPS", "2")
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(B, seed=3)
+    trim = sc.hover_trim()
+    mpc = _mpc(N, B)
+    orc = co.BatchRTI(P, B)
+    mpc.reset(x0, trim)
+    orc.reset(x0, trim)
+    X_before = mpc.iterate()[0].clone()
+    x0 = x0.copy()
+    x0[1, 7] = np.nan
+    yref[3, 2] = np.inf
+    x0[5, 2] = 1e6
+    u0, X, U, st = mpc.solve(x0, yref)
+    uo, Xo, Uo, sto = orc.solve(x0, yref)
+    st = st.cpu().numpy()
+    assert (st == sto).all() and list(st[[1, 3, 5]]) == [1, 1, 3]
+    assert (mpc.iters.cpu().numpy() == orc.iters).all()
+    for i in (1, 3, 5):
+        assert torch.equal(X[i], X_before[i])
+    ok = sto == 0
+    assert ok.sum() >= B - 4
+    assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
