@@ -2,7 +2,11 @@
 """Join an ncu report's per-SASS-instruction samples with nvdisasm line info and print a
 per-source-line profile of one kernel (samples, stall mix, executed instructions).
 
-    python tools/ncu_lines.py gpurun_out/prof.ncu-rep mpc_blaster_b200/lib/libmpcb.so qp_kernelILi17
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep mpc_blaster_b200/lib/libmpcb.so qp_kernelILi17ELi6ELi1ELi2ELi1E
+
+The pattern must select ONE function of the library (mangled-name substring; several template instantiations
+share a prefix): with more than one match the tool stops and lists them -- their line tables would overwrite
+each other.  Run it from a checkout of the sources the library was built from.
 """
 import csv
 import io
@@ -39,6 +43,9 @@ def main():
         sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
     line_of = {}
     cur, infn = None, False
+    matches = [l.strip() for l in sass.splitlines() if l.startswith(".text.") and pat in l]
+    if len(matches) != 1:
+        sys.exit(f"pattern {pat!r} selects {len(matches)} functions, need exactly one:\n  " + "\n  ".join(matches))
     for l in sass.splitlines():
         if l.startswith(".text."):
             infn = pat in l
