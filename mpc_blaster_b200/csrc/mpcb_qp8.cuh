@@ -25,14 +25,20 @@ struct Qp8Group {
     using L = Layout<NX, NU>;
     alignas(16) double rec[L::O_Z];  // head of a stage record: [BAt | Lu | invd | lvec | rb]
     double lxx[L::LXX];              // factor of P_{k+1} / P_k, row-major, zero upper triangle
-    double vrow[2][L::NXP];          // pivot row broadcast (double buffered)
-    // Three pairs of arrays are never live at the same time and share storage (19.1 -> 18.1 KB per QUAD12 warp:
-    // 12 instead of 11 warps per SM; 22.5 -> 20.9 KB and 9 -> 10 warps for QUAT13):
+    // Arrays that are never live at the same time share storage (BLASTER17: 36.0 -> 31.9 KB per warp, 7 instead of 6
+    // warps per SM; QUAD12: 19.1 -> 16.8 KB, 12 instead of 11; every hand-over has a warp_sync between the last read
+    // of one and the first write of the other):
+    union {
+        double vrow[2][L::NXP];      // pivot row broadcast (double buffered): live inside the Householder loop only
+        struct {
+            double sT1[L::NXP];      // temporary L' r of t2 = P r + p: dead before the loop
+            double cPv[L::NXP];      // carried p_{k+1}: consumed by t2 before the loop, rewritten after it
+        };
+    };
     union {
         double vz[L::NZP];           // a stage vector every lane of the group reads (z_k or dz_k): dead once r_k and the carry are formed
         double hd[L::NZP];           // Hd_k of every row, written after the W product for the pivot loop
     };
-    double ds[L::NZP];               // sqrt(Hd_k) of every row (pivot loop)
     union {
         double cPi[L::NXP];          // backward sweep S1: pi_{k+1}
         double cDx[L::NXP];          // forward sweeps: dx_k (zeroed at their start)
@@ -41,12 +47,15 @@ struct Qp8Group {
         double sRb[L::NXP];          // r_k (S1) / dx_{k+1} (S4): last read when sT1 is formed ...
         double sT2[L::NXP];          // ... before t2 = P r + p is written (a sync lies between)
     };
-    double cZx[L::NXP], cPv[L::NXP], sT1[L::NXP];  // carried: dx-part of z_{k+1}, p_{k+1}; temporary L' r
+    double cZx[L::NXP];              // carried dx-part of z_{k+1}
+    // sqrt(Hd_k) of every row (pivot loop) lives in the [lvec | rb] slice of `rec`, which the backward sweep S1 does not use
+    static_assert(L::O_Z - L::O_LVEC >= L::NZP, "rec[lvec|rb] must hold one entry per row");
+    MPCB_HD double *ds() { return rec + L::O_LVEC; }
     // Pad so that consecutive groups are 32 bytes (mod 128) apart: the four groups of a warp then hit
     // distinct banks when each broadcasts one word to its lanes, and a 64-byte run per group splits into
     // the minimal two wavefronts.  (QUAD12's unpadded group is a multiple of 128 bytes: every broadcast
     // was a 4-way bank conflict, 43 % of all shared-memory wavefronts in ncu.)
-    static constexpr int kBody = L::O_Z + L::LXX + 2 * L::NXP + 2 * L::NZP + 5 * L::NXP;
+    static constexpr int kBody = L::O_Z + L::LXX + 2 * L::NXP + L::NZP + 3 * L::NXP;
     double pad[(4 - kBody % 16 + 16) % 16 == 0 ? 16 : (4 - kBody % 16 + 16) % 16];
 };
 static_assert(sizeof(Qp8Group<17, 6>) % 128 == 32 && sizeof(Qp8Group<12, 4>) % 128 == 32 && sizeof(Qp8Group<13, 4>) % 128 == 32,
@@ -670,7 +679,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
             }
             MPCB_UNROLL
             for (int t = 0; t < NT; t++)
-                if (s + kLPI * t < NZ) { sm.hd[s + kLPI * t] = Hd[t]; sm.ds[s + kLPI * t] = dsq[t]; }
+                if (s + kLPI * t < NZ) { sm.hd[s + kLPI * t] = Hd[t]; sm.ds()[s + kLPI * t] = dsq[t]; }
             const int jend = (k == 0) ? NU : NZ;
             double sig = 1.0;
             MPCB_UNROLL
@@ -685,7 +694,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                         for (int c = 0; c < NX; c++) vr[c] = w[tj][c];
                     }
                     warp_sync();
-                    const double hdj = sm.hd[j], dsj = sm.ds[j];
+                    const double hdj = sm.hd[j], dsj = sm.ds()[j];
                     double v[NX];
                     MPCB_UNROLL
                     for (int c = 0; c < NX; c++) v[c] = vr[c];
