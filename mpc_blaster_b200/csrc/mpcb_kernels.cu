@@ -489,11 +489,12 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         h->throughput_batch = tb ? atoi(tb) : 4096;
         // four-instances-per-warp kernel (persistent, groups refilled from a work counter, next stage's record
         // prefetched into L2): measured faster than the one-instance kernel from ~2,600 instances on for QUAD12
-        // (576 k against 487 k solves/s at 3,072; 987 k against 621 k at 65,536) and from ~12,000 on for BLASTER17
-        // (380 k against 378 k at 12,288; 401 k against 383 k at 16,384; 439 k against 393 k at 65,536).
+        // (576 k against 487 k solves/s at 3,072; 1.00 M against 621 k at 65,536) and from two of its waves
+        // (148 SMs x 7 warps x 4 = 4,144 instances each) on for BLASTER17 (390 k against 362 k at 8,192; 378 k
+        // against 374 k at 10,240; 424 k against 383 k at 16,384; 460 k against 393 k at 65,536).
         // MPCB_QP8_BATCH=<chunk size> overrides the threshold.
         const char *q8 = getenv("MPCB_QP8_BATCH");
-        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 17 ? 12288 : 3072);
+        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 17 ? 8192 : 3072);
     }
     const size_t B = (size_t)h->max_batch;
     const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;
