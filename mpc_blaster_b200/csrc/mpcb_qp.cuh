@@ -24,6 +24,13 @@
 
 namespace mpcb {
 
+// Complementarity above which the latency variant (NSLOT = 2) factorises the stage matrix in normal-equations form
+// (Gram matrix + Cholesky) instead of the Householder LQ; -DMPCB_GRAM_MU=1e30 switches it off (tools/ab.py).
+// Measured at 1,024 instances: -7.8 % launch time at 1e-4 (BLASTER17; QUAD12 -8.8 %), -10.2 % at 1e-6; the single-buffer
+// throughput variant (168-register cap, 12 warps per SM) spills with it and is 18 % slower, so it keeps the LQ throughout.
+#ifndef MPCB_GRAM_MU
+#define MPCB_GRAM_MU 1e-4
+#endif
 constexpr double kMuDiverge = 1e2;  // infeasibility test: mu > kMuDiverge * mu0 (the CPU checkers apply the same test; no feasible instance of the test scenarios exceeds 3 * mu0)
 
 // Per-warp shared memory: two stage-record images (same offsets as the global record) plus
@@ -504,6 +511,74 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 for (int j = c; j < NX; j++) a += brow[j] * sm.Lxx[j * NX + c];
                 w[c] = a;
             }
+            T Lu[NU], invd[NU];
+            constexpr bool kGramFactor = (NSLOT == 2) && (MPCB_GRAM_MU < 1e29);
+            if (kGramFactor && mu > T(MPCB_GRAM_MU)) {
+            // Early interior-point iterations (mu > MPCB_GRAM_MU): the normal-equations form, as HPIPM's default
+            // Riccati -- M = diag(Hd) + W W' formed row by row (lane i owns row i, the rows of W broadcast from
+            // shared memory), then a right-looking Cholesky, fully unrolled so that row i stays in registers: per
+            // pivot one shared-memory round (column j, unscaled, diagonal included), one rsqrt, 22-j FMAs.  About
+            // half the instructions of the Householder LQ below, but it loses eps*|P| where the LQ loses
+            // eps*sqrt|P|, and |P| grows like 1/mu on active state bounds: used on every iteration it changes
+            // iteration counts and moves u by up to 8e-6 against the checker; confined to mu > 1e-4 the solutions
+            // agree with the all-LQ solver's to the same 1e-11 (emulator, tests/test_kernel_emulation.py).
+            {
+                constexpr int LDW = (NX + 1) & ~1;  // rows of the W image stay 16-byte aligned
+                static_assert(NZ * LDW <= L::STAGE - L::O_C1, "the W image must fit the part of the record image this sweep does not fetch");
+                static_assert(2 * L::NZP <= L::NZ * L::NUP, "column buffer must fit sm.Lcol");
+                if (lane >= NZ) {
+                    MPCB_UNROLL
+                    for (int c = 0; c < NX; c++) w[c] = T(0);
+                }
+                T *Wsh = sm.slot[half] + L::O_C1;
+                sp_row_store<0, NX>(sptr_of(Wsh + (lane < NZ ? lane : 0) * LDW), w, lane < NZ);
+                warp_sync();
+                const sptr w0 = sptr_of(Wsh);
+                T m[NZ + 1];
+                MPCB_UNROLL
+                for (int c = 0; c <= NZ; c++) m[c] = T(0);
+                auto gram = [&](auto C) {
+                    constexpr int c = decltype(C)::value;
+                    T v[NX];
+                    sp_row_load<0, NX>(sptr_add(w0, c * LDW), v);
+                    T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+                    MPCB_UNROLL
+                    for (int i = 0; i + 3 < NX; i += 4) { d0 += v[i] * w[i]; d1 += v[i + 1] * w[i + 1]; d2 += v[i + 2] * w[i + 2]; d3 += v[i + 3] * w[i + 3]; }
+                    MPCB_UNROLL
+                    for (int i = NX & ~3; i < NX; i++) d0 += v[i] * w[i];
+                    m[c] = ((d0 + d1) + (d2 + d3)) + (lane == c ? Hd : T(0));
+                };
+                const sptr cb0 = sptr_of(sm.Lcol);
+                const sptr cbl = sptr_add(cb0, lane < NZ ? lane : 0);
+                T sig = T(1);
+                auto pivot = [&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    constexpr int par = (j & 1) * L::NZP;
+                    sp_st1<par>(cbl, m[j], lane < NZ);
+                    warp_sync();
+                    T a[NZ + 1];
+                    static_for<(j & ~1), NZ, 2>([&](auto Cc) {
+                        constexpr int c = decltype(Cc)::value;
+                        sp_ld2<par + c>(cb0, a[c], a[c + 1]);
+                    });
+                    const T rs = fast_rsqrt(a[j]);
+                    sig = a[j] * rs;
+                    const T f = m[j] * (rs * rs);
+                    const T lij = m[j] * rs;
+                    MPCB_UNROLL
+                    for (int c = j + 1; c < NZ; c++) m[c] -= f * a[c];
+                    const T val = (lane == j) ? sig : (lane > j ? lij : T(0));
+                    if constexpr (j < NU) { Lu[j] = val; invd[j] = rs; }
+                    else { if (lane >= j && lane < NZ) sm.Lxx[(lane - NU) * NX + (j - NU)] = val; }
+                };
+                static_for<0, NU>(gram);
+                if (k > 0) static_for<NU, NZ>(gram);
+                static_for<0, NU>(pivot);
+                if (k > 0) static_for<NU, NZ>(pivot);
+                last_sig = sig;
+            }
+            warp_sync();
+            } else {
             const T dsq = sqrt(Hd);
             if (lane < NZ) { sm.hd[lane] = Hd; sm.ds[lane] = dsq; }  // visible after the first pivot's warp_sync
             // Householder LQ of [diag(dsq) | W], one pivot row per step:
@@ -574,9 +649,10 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             }
             last_sig = sig;
             warp_sync();
-            T Lu[NU], invd[NU];
+
             MPCB_UNROLL
             for (int c = 0; c < NU; c++) { Lu[c] = sm.Lcol[(lane < NZ ? lane : 0) * L::NUP + c]; invd[c] = sm.Linv[c]; }
+            }
             // affine backward vectors: l = q + [B A]' t2
             T l0 = q, l1 = T(0);
             MPCB_UNROLL

@@ -10,7 +10,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mpc_blaster_b200", "csrc")
-LIB = os.path.join(HERE, "_build", "libmpcb_emu.so")
+# MPCB_EMU_DEFINES="A,B=1": host build of an experimental -D variant of the kernels (tools/ab.py's CPU counterpart)
+_DEFS = [d for d in os.environ.get("MPCB_EMU_DEFINES", "").split(",") if d]
+LIB = os.path.join(HERE, "_build", "libmpcb_emu" + "".join("_" + d.replace("=", "") for d in _DEFS) + ".so")
 
 
 class Params(C.Structure):
@@ -31,7 +33,7 @@ def build(force=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMPCB_HOST_EMU", "-ffp-contract=off", "-fPIC", "-shared",
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMPCB_HOST_EMU", "-ffp-contract=off", "-fPIC", "-shared"] + ["-D" + d for d in _DEFS] + [
                            "-I" + HERE, "-I" + CSRC, "-x", "c++", srcs[0], "-o", LIB])
     return LIB
 
