@@ -537,6 +537,42 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 T m[NZ + 1];
                 MPCB_UNROLL
                 for (int c = 0; c <= NZ; c++) m[c] = T(0);
+#ifdef MPCB_GRAM_WINDOW
+                // Experiment prepared at the end of round 1, not yet measured on a GPU (isolated in
+                // tools/ubench_gram.cu): M is symmetric, so the entries (i, (i - d) mod NZ), d = 0 .. NZ/2, over all lanes i
+                // cover every pair -- NZ/2 + 1 dot products per lane instead of NZ, in a rolled loop; the results go
+                // through a packed lower triangle (rows padded to even length) in the unused tail of the OTHER record
+                // image and every lane reads its row back.
+                {
+                    constexpr int ND = NZ / 2 + 1;
+                    auto row_off = [](int r) { return 2 * (r >> 1) * ((r >> 1) + 1) + (r & 1) * (2 * (r >> 1) + 2); };
+                    static_assert(2 * ((NZ - 1) >> 1) * (((NZ - 1) >> 1) + 1) + ((NZ - 1) & 1) * (2 * ((NZ - 1) >> 1) + 2) + L::NZP <= L::STAGE - L::O_C1,
+                                  "the packed triangle must fit the unused tail of the other record image");
+                    T *Msh = sm.slot[half ^ 1] + L::O_C1;
+                    const int ri = lane < NZ ? lane : 0;
+                    MPCB_PRAGMA_UNROLL2
+                    for (int d = 0; d < ND; d++) {
+                        int c = ri - d;
+                        if (c < 0) c += NZ;
+                        T v[NX];
+                        sp_row_load<0, NX>(sptr_add(w0, c * LDW), v);
+                        T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+                        MPCB_UNROLL
+                        for (int i = 0; i + 3 < NX; i += 4) { d0 += v[i] * w[i]; d1 += v[i + 1] * w[i + 1]; d2 += v[i + 2] * w[i + 2]; d3 += v[i + 3] * w[i + 3]; }
+                        MPCB_UNROLL
+                        for (int i = NX & ~3; i < NX; i++) d0 += v[i] * w[i];
+                        const T val = ((d0 + d1) + (d2 + d3)) + (d == 0 ? Hd : T(0));
+                        const int rr = ri > c ? ri : c, qq = ri > c ? c : ri;
+                        if (lane < NZ) Msh[row_off(rr) + qq] = val;
+                    }
+                    warp_sync();
+                    const sptr mrow = sptr_of(Msh + row_off(ri));
+                    static_for<0, NZ, 2>([&](auto Cc) {
+                        constexpr int c = decltype(Cc)::value;
+                        sp_ld2<c>(mrow, m[c], m[c + 1]);  // entries past the row's own length belong to later rows: never used
+                    });
+                }
+#else
                 auto gram = [&](auto C) {
                     constexpr int c = decltype(C)::value;
                     T v[NX];
@@ -548,6 +584,9 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     for (int i = NX & ~3; i < NX; i++) d0 += v[i] * w[i];
                     m[c] = ((d0 + d1) + (d2 + d3)) + (lane == c ? Hd : T(0));
                 };
+                static_for<0, NU>(gram);
+                if (k > 0) static_for<NU, NZ>(gram);
+#endif
                 const sptr cb0 = sptr_of(sm.Lcol);
                 const sptr cbl = sptr_add(cb0, lane < NZ ? lane : 0);
                 T sig = T(1);
@@ -571,8 +610,6 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     if constexpr (j < NU) { Lu[j] = val; invd[j] = rs; }
                     else { if (lane >= j && lane < NZ) sm.Lxx[(lane - NU) * NX + (j - NU)] = val; }
                 };
-                static_for<0, NU>(gram);
-                if (k > 0) static_for<NU, NZ>(gram);
                 static_for<0, NU>(pivot);
                 if (k > 0) static_for<NU, NZ>(pivot);
                 last_sig = sig;
