@@ -626,7 +626,12 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             // NOT unrolled: its body (~2 KB of SASS) then stays in the L0 instruction cache, which
             // matters at 1-2 resident warps per scheduler.  Column j of L goes to shared memory
             // (sm.Lcol, [NZ][NZ+1]); at stage 0 only the u-block is needed (x_0 is pinned).
+#ifdef MPCB_GRAM_X
+            const bool gram_x = (NSLOT == 2) && mu > T(MPCB_GRAM_X);  // the x-block then follows below in normal-equations form
+            const int jend = (k == 0 || gram_x) ? NU : NZ;
+#else
             const int jend = (k == 0) ? NU : NZ;
+#endif
             T sig = T(1);
             if (lane >= NZ) {
                 MPCB_UNROLL
@@ -686,6 +691,60 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             }
             last_sig = sig;
             warp_sync();
+#ifdef MPCB_GRAM_X
+            // Experiment prepared at the end of round 1, parity-checked in the host emulator, not yet measured on a GPU
+            // (DESIGN.md section 9).  The cancellation that rules the normal equations out near the solution sits in
+            // the elimination of the INPUTS (Schur complement over the thrusts); once the
+            // NU input pivots have been done by Householder reflections, what is left for the states is
+            // diag(Hd_x) + W_x W_x' with the barrier terms on the diagonal only, which a Cholesky handles.  So: NU LQ
+            // pivots above, then Gram matrix + unrolled Cholesky on the NX state rows (lane NU + r owns row r).
+            if (k > 0 && gram_x) {
+                constexpr int LDW = (NX + 1) & ~1;
+                static_assert(NX * LDW <= L::STAGE - L::O_C1, "the W image must fit the part of the record image this sweep does not fetch");
+                static_assert(2 * L::NXP <= 2 * L::NXP, "column buffer = sm.vrow");
+                const bool xl = lane >= NU && lane < NZ;
+                const int r = xl ? lane - NU : 0;
+                T *Wsh = sm.slot[half] + L::O_C1;
+                sp_row_store<0, NX>(sptr_of(Wsh + r * LDW), w, xl);
+                warp_sync();
+                const sptr w0 = sptr_of(Wsh);
+                T m[NX + 1];
+                m[NX] = T(0);
+                static_for<0, NX>([&](auto C) {
+                    constexpr int c = decltype(C)::value;
+                    T v[NX];
+                    sp_row_load<0, NX>(sptr_add(w0, c * LDW), v);
+                    T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
+                    MPCB_UNROLL
+                    for (int i = 0; i + 3 < NX; i += 4) { d0 += v[i] * w[i]; d1 += v[i + 1] * w[i + 1]; d2 += v[i + 2] * w[i + 2]; d3 += v[i + 3] * w[i + 3]; }
+                    MPCB_UNROLL
+                    for (int i = NX & ~3; i < NX; i++) d0 += v[i] * w[i];
+                    m[c] = ((d0 + d1) + (d2 + d3)) + ((xl && r == c) ? Hd : T(0));
+                });
+                const sptr cb0 = sptr_of(sm.vrow[0]);
+                const sptr cbl = sptr_add(cb0, r);
+                static_for<0, NX>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    constexpr int par = (j & 1) * L::NXP;
+                    sp_st1<par>(cbl, m[j], xl);
+                    warp_sync();
+                    T a[NX + 1];
+                    static_for<(j & ~1), NX, 2>([&](auto Cc) {
+                        constexpr int c = decltype(Cc)::value;
+                        sp_ld2<par + c>(cb0, a[c], a[c + 1]);
+                    });
+                    const T rs = fast_rsqrt(a[j]);
+                    sig = a[j] * rs;
+                    const T f = m[j] * (rs * rs);
+                    const T lij = m[j] * rs;
+                    MPCB_UNROLL
+                    for (int c = j + 1; c < NX; c++) m[c] -= f * a[c];
+                    if (xl && r >= j) sm.Lxx[r * NX + j] = (r == j) ? sig : lij;
+                });
+                last_sig = sig;
+                warp_sync();
+            }
+#endif
 
             MPCB_UNROLL
             for (int c = 0; c < NU; c++) { Lu[c] = sm.Lcol[(lane < NZ ? lane : 0) * L::NUP + c]; invd[c] = sm.Linv[c]; }

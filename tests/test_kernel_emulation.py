@@ -190,14 +190,16 @@ def test_hybrid_factorisation_agrees_with_householder_only_build(tmp_path):
     script = tmp_path / "case.py"
     script.write_text(_HYBRID_CASE)
     res = {}
-    for tag, defs in (("hybrid", ""), ("lq", "MPCB_GRAM_MU=1e30")):
+    # "gramx": the prepared follow-up (-DMPCB_GRAM_X=<mu>: LQ for the input pivots, normal equations for the state block
+    # while mu > 1e-7), off by default until it has been measured on a GPU -- kept building and agreeing here
+    for tag, defs in (("hybrid", ""), ("lq", "MPCB_GRAM_MU=1e30"), ("gramx", "MPCB_GRAM_X=1e-7")):
         out = tmp_path / f"{tag}.npz"
         env = dict(os.environ, MPCB_EMU_DEFINES=defs)
         subprocess.check_call([sys.executable, str(script), os.path.dirname(here), os.path.join(here, "emu"), str(out)], env=env)
         res[tag] = np.load(out)
     assert sorted(res["hybrid"].files) == sorted(res["lq"].files) and len(res["lq"].files) == 6
-    for k in res["lq"].files:
-        a, b = res["hybrid"][k], res["lq"][k]
-        assert a[0] == b[0] == 0 and a[1] == b[1], k           # status, IPM iterations
+    for k, tag in ((k, tag) for k in res["lq"].files for tag in ("hybrid", "gramx")):
+        a, b = res[tag][k], res["lq"][k]
+        assert a[0] == b[0] == 0 and a[1] == b[1], (k, tag)    # status, IPM iterations
         # measured: hybrid 2e-12; Gram on every iteration 1e-9 on these cases and 8e-6 on cold random set-points
         assert np.abs(a[2:] - b[2:]).max() < 5e-11, (k, np.abs(a[2:] - b[2:]).max())
