@@ -28,6 +28,8 @@ namespace mpcb {
 // (Gram matrix + Cholesky) instead of the Householder LQ; -DMPCB_GRAM_MU=1e30 switches it off (tools/ab.py).
 // Measured at 1,024 instances: -7.8 % launch time at 1e-4 (BLASTER17; QUAD12 -8.8 %), -10.2 % at 1e-6; the single-buffer
 // throughput variant (168-register cap, 12 warps per SM) spills with it and is 18 % slower, so it keeps the LQ throughout.
+// Also only while mu <= mu0: on an infeasible QP the multipliers diverge (mu climbs towards the 100 * mu0 exit) and the Gram
+// matrix loses a pivot before the LQ does -- the instance would end with ST_QPFAIL where the checkers report ST_MINSTEP.
 #ifndef MPCB_GRAM_MU
 #define MPCB_GRAM_MU 1e-4
 #endif
@@ -513,7 +515,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             }
             T Lu[NU], invd[NU];
             constexpr bool kGramFactor = (NSLOT == 2) && (MPCB_GRAM_MU < 1e29);
-            if (kGramFactor && mu > T(MPCB_GRAM_MU)) {
+            if (kGramFactor && mu > T(MPCB_GRAM_MU) && mu <= (T)P.ipm_mu0) {
             // Early interior-point iterations (mu > MPCB_GRAM_MU): the normal-equations form, as HPIPM's default
             // Riccati -- M = diag(Hd) + W W' formed row by row (lane i owns row i, the rows of W broadcast from
             // shared memory), then a right-looking Cholesky, fully unrolled so that row i stays in registers: per

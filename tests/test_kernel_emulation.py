@@ -203,3 +203,20 @@ def test_hybrid_factorisation_agrees_with_householder_only_build(tmp_path):
         assert a[0] == b[0] == 0 and a[1] == b[1], (k, tag)    # status, IPM iterations
         # measured: hybrid 2e-12; Gram on every iteration 1e-9 on these cases and 8e-6 on cold random set-points
         assert np.abs(a[2:] - b[2:]).max() < 5e-11, (k, np.abs(a[2:] - b[2:]).max())
+
+
+def test_emulated_kernel_infeasible_instance_keeps_the_checkers_status():
+    """An infeasible linearised QP (N = 40 random set-point, zero iterate): the multipliers diverge and the
+    solve must end with the checker's status after the checker's number of iterations.  With the
+    normal-equations factorisation allowed at mu > mu0 this instance broke down one iteration early with the
+    QP-failure status instead of the min-step status -- hence the `mu <= mu0` guard in mpcb_qp.cuh."""
+    N = 40
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(40, seed=1234)
+    p = bo.default_params()
+    i = 19
+    X, U = np.zeros((N + 1, P.nx)), np.zeros((N, P.nu))
+    st, it, _, _ = eb.rti_solve(P, X, U, x0[i], yref[i], p)
+    c = co.BatchRTI(P, 1, nthreads=1)
+    _, _, _, stc = c.solve(x0[i:i + 1], yref[i], p)
+    assert stc[0] != 0 and st == stc[0] and it == c.iters[0]
