@@ -629,7 +629,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             // matters at 1-2 resident warps per scheduler.  Column j of L goes to shared memory
             // (sm.Lcol, [NZ][NZ+1]); at stage 0 only the u-block is needed (x_0 is pinned).
 #ifdef MPCB_GRAM_X
-            const bool gram_x = (NSLOT == 2) && mu > T(MPCB_GRAM_X);  // the x-block then follows below in normal-equations form
+            const bool gram_x = (NSLOT == 2) && mu > T(MPCB_GRAM_X) && mu <= (T)P.ipm_mu0;  // the x-block then follows below in normal-equations form
             const int jend = (k == 0 || gram_x) ? NU : NZ;
 #else
             const int jend = (k == 0) ? NU : NZ;
