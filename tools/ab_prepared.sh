@@ -25,4 +25,8 @@ for v in gramx gramx_only gramwin mu5; do
     echo "== GPU suite with $v" >> $OUT
     MPCB_LIB_OVERRIDE=$PWD/mpc_blaster_b200/lib/libmpcb_$v.so timeout 200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 >> $OUT
 done
-tail -20 $OUT
+# crossover between the latency variant (now with the hybrid factorisation) and the single-buffer throughput variant
+echo "== MPCB_THROUGHPUT_BATCH: default (4096) against latency variant forced" >> $OUT
+python tools/ab.py run base --points "4096,20,17,rand;6144,20,17,rand" >> $OUT 2>&1
+MPCB_THROUGHPUT_BATCH=100000000 python tools/ab.py run base --points "4096,20,17,rand;6144,20,17,rand" >> $OUT 2>&1
+tail -30 $OUT
