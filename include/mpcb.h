@@ -25,6 +25,10 @@
  * Return value: 0 on success, negative on API misuse or CUDA failure (message through
  * mpcb_last_error).  Per-instance solver outcome goes to status[B], mirroring acados'
  * codes: 0 success, 1 NaN, 2 max-iter, 3 min-step, 4 QP failure.
+ *
+ * Failed solves (status != 0): the stored iterate of that instance is left untouched, so the u0 / X / U returned for it
+ * are the PREVIOUS iterate's (stale) values -- check status (mpcb_closed_loop counts such steps in n_fail).  With
+ * mpcb_config.strict_reference = 1 a max-iter solve (status 2) does apply its last interior-point iterate, as acados does.
  */
 #ifndef MPCB_H
 #define MPCB_H
@@ -69,6 +73,19 @@ typedef struct mpcb_config {
     int32_t max_batch;    /* capacity of the persistent iterate (instances) */
     int32_t ws_batch;     /* instances of solver workspace resident at once (0 = auto) */
     int32_t device;       /* CUDA device ordinal, -1 = current */
+    /* Reference-semantics switch.  0 (default): the throughput-oriented stopping rules of DESIGN.md section 2 -- linear
+     * residuals tracked through their exact-arithmetic decay and confirmed explicitly before success is reported,
+     * early exit (status 3) when the multipliers diverge, a failed QP leaves the iterate untouched.  1: what the
+     * reference's stack does -- explicitly evaluated residual norms (stationarity included) in the stopping test, no
+     * divergence exit (the interior point runs to ipm_max_iter; the reference sets qp_solver_iter_max = 500,
+     * blastermodel.py:279), and the last interior-point iterate is applied when that cap is hit (acados SQP_RTI takes
+     * the QP solver's last iterate on max-iter; the reference script ignores the status, simulation_blaster.py:80).
+     * Strict solves always run the one-instance-per-warp kernel. */
+    int32_t strict_reference;
+    /* Kernel selection by workspace-chunk size, 0 = measured defaults: chunks of at least
+     * throughput_batch instances use the single-buffer variant of the one-instance-per-warp kernel, chunks of at least
+     * qp8_batch the four-instances-per-warp kernel.  qp8_warps > 0 caps that kernel's grid (test hook). */
+    int32_t throughput_batch, qp8_batch, qp8_warps;
 } mpcb_config;
 
 typedef struct mpcb_handle mpcb_handle;
@@ -104,12 +121,21 @@ int mpcb_solve(mpcb_handle *h, const double *x0, const double *yref, int yref_mo
 int mpcb_solve_host(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
                     double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B);
 
-/* `sqp_iters` SQP iterations on the same (x0, yref, p) -- each one re-linearises about the iterate
- * the previous one produced (SQP instead of SQP_RTI; the reference's options carry
- * nlp_solver_max_iter = 100 but select SQP_RTI, blastermodel.py:278).  status/iters are those of
- * the last iteration. */
+/* Multi-iteration SQP on the same (x0, yref, p): every iteration re-linearises about the iterate the previous one
+ * produced (nlp_solver_type SQP instead of SQP_RTI; the reference's options carry nlp_solver_max_iter = 100 and
+ * nlp_solver_tol_stat/eq/ineq/comp = 1e-6 but select SQP_RTI: blastermodel.py:278, acados_ocp_blasterModel.json
+ * solver_options).
+ *   tol != NULL: tol[4] = {stat, eq, ineq, comp}.  Per instance, acados' SQP loop: linearise; evaluate the NLP residuals
+ *     (inf-norms of the Lagrangian gradient with the last QP's multipliers, of the dynamics defect, of the bound
+ *     violation and of the complementarity products); stop when all four are within tolerance; otherwise solve the QP and
+ *     take the full step; at most max_iter QPs.  Finished instances are skipped by the kernels.  status[B]: 0 converged,
+ *     2 max_iter reached, 4 a QP failed (its own status was not 0), 1 NaN; iters[B]: interior-point iterations summed
+ *     over the QPs; sqp_iters[B]: QPs solved; nlp_res[B,4]: the last evaluated residuals (the final iterate's).
+ *   tol == NULL: exactly max_iter SQP iterations without a residual test; status / iters are those of the last QP.
+ * Outputs may be NULL. */
 int mpcb_solve_sqp(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
-                   int sqp_iters, double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B, void *stream);
+                   int max_iter, const double *tol, double *u0, double *X, double *U, int32_t *status, int32_t *iters,
+                   int32_t *sqp_iters, double *nlp_res, int B, void *stream);
 
 /* Shift the stored iterate one stage forward (X_k <- X_{k+1}, U_k <- U_{k+1}, last stage repeated):
  * the standard warm start between control steps.  The reference's scripts never shift
@@ -138,6 +164,15 @@ int mpcb_set_iterate(mpcb_handle *h, const double *X, const double *U, int B, vo
 /* Test hook: run only the rollout + sensitivity kernel for instances [0,B) and return
  * BAt[B,N,nz,nx] = [B_k'; A_k'] and b[B,N,nx] (device pointers). */
 int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BAt, double *b, int B, void *stream);
+
+/* Test hook: the interior-point iterate the last mpcb_solve ended with and the QP it solved, copied out of the solver
+ * workspace (valid right after an mpcb_solve of B <= ws_batch instances; nothing is recomputed).  Device pointers, any
+ * may be NULL: z[B,N+1,nz] (z_k = [du_k; dx_k], dx_0 pinned), pi[B,N+1,nx] (pi_0 unused), slacks tl/tu and multipliers
+ * ll/lu [B,N+1,nz] (zero where a component has no bound), the bounds on the increments lb/ub [B,N+1,nz] (-inf/+inf where
+ * absent), the cost gradient g[B,N+1,nz], and the linearisation BAt[B,N,nz,nx] = [B_k'; A_k'], b[B,N,nx] (both or
+ * neither).  tests/ evaluate the explicit KKT residuals of the GPU's solution from these. */
+int mpcb_debug_qp(mpcb_handle *h, double *z, double *pi, double *tl, double *tu, double *ll, double *lu, double *lb, double *ub,
+                  double *g, double *BAt, double *b, int B, void *stream);
 
 /* Profiling aid for bench.py: when enabled, CUDA events are recorded on the launching stream
  * around the rollout kernel and the QP kernel of each solve (first workspace chunk);

@@ -21,14 +21,16 @@ class MpcbConfig(C.Structure):
                 ("lbx", C.c_double * 17), ("ubx", C.c_double * 17), ("lbu", C.c_double * 6), ("ubu", C.c_double * 6),
                 ("ipm_max_iter", C.c_int32), ("ipm_mu0", C.c_double), ("ipm_thr0", C.c_double),
                 ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double),
-                ("alpha_min", C.c_double), ("dtype", C.c_int32), ("max_batch", C.c_int32), ("ws_batch", C.c_int32), ("device", C.c_int32)]
+                ("alpha_min", C.c_double), ("dtype", C.c_int32), ("max_batch", C.c_int32), ("ws_batch", C.c_int32), ("device", C.c_int32),
+                ("strict_reference", C.c_int32), ("throughput_batch", C.c_int32), ("qp8_batch", C.c_int32), ("qp8_warps", C.c_int32)]
 
 
 # every symbol include/mpcb.h declares
 EXPORTS = ["mpcb_config_default", "mpcb_create", "mpcb_destroy", "mpcb_last_error", "mpcb_nx", "mpcb_nu", "mpcb_horizon",
            "mpcb_reset", "mpcb_solve", "mpcb_solve_host", "mpcb_plant_step", "mpcb_closed_loop", "mpcb_cost",
            "mpcb_get_iterate", "mpcb_set_iterate", "mpcb_debug_linearize", "mpcb_kernel_launches", "mpcb_command_map",
-           "mpcb_profile", "mpcb_last_kernel_ms", "mpcb_fp64_peak", "mpcb_solve_sqp", "mpcb_shift", "mpcb_poc_jacobians"]
+           "mpcb_profile", "mpcb_last_kernel_ms", "mpcb_fp64_peak", "mpcb_solve_sqp", "mpcb_shift", "mpcb_poc_jacobians",
+           "mpcb_debug_qp"]
 
 _lib = None
 
@@ -61,7 +63,8 @@ def load() -> C.CDLL:
         getattr(lib, f).argtypes = [vp]
     lib.mpcb_reset.argtypes = [vp, dp, dp, C.c_int, C.c_int, vp]
     lib.mpcb_solve.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip, C.c_int, vp]
-    lib.mpcb_solve_sqp.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, C.c_int, dp, dp, dp, ip, ip, C.c_int, vp]
+    lib.mpcb_solve_sqp.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, C.c_int, dp, dp, dp, dp, ip, ip, ip, dp, C.c_int, vp]
+    lib.mpcb_debug_qp.argtypes = [vp] + [dp] * 11 + [C.c_int, vp]
     lib.mpcb_shift.argtypes = [vp, C.c_int, vp]
     lib.mpcb_solve_host.argtypes = [vp, dp, dp, C.c_int, dp, C.c_int, dp, dp, dp, ip, ip, C.c_int]
     lib.mpcb_plant_step.argtypes = [vp, dp, dp, dp, C.c_int, dp, C.c_int, vp]

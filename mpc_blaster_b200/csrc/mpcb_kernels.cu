@@ -20,7 +20,7 @@ using namespace mpcb;
 namespace {
 
 std::atomic<int64_t> g_launches{0};
-std::string g_create_error;
+thread_local std::string g_create_error;  // message of the last failed create / stateless call on this thread
 
 // ------------------------------------------------------------------ kernels
 __device__ __forceinline__ const double *param_ptr(const double *p, int p_mode, int inst, int k, int N)
@@ -34,7 +34,8 @@ __device__ __forceinline__ const double *param_ptr(const double *p, int p_mode, 
 template <int NX, int NU>
 __global__ void __launch_bounds__(128) linearize_kernel(const __grid_constant__ Params P, const double *__restrict__ X,
                                                         const double *__restrict__ U, const double *__restrict__ p,
-                                                        int p_mode, double *__restrict__ ws, int inst0, int B)
+                                                        int p_mode, double *__restrict__ ws, int inst0, int B,
+                                                        const int32_t *__restrict__ skip)
 {
     using L = Layout<NX, NU>;
     const int N = P.N;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(128) linearize_kernel(const __grid_constant__ 
     if (gw >= (long long)B * N) return;
     const int li = (int)(gw / N), k = (int)(gw % N);
     const int inst = inst0 + li;
+    if (skip && skip[inst]) return;  // SQP: this instance has converged
     const double *Xi = X + (size_t)inst * (N + 1) * NX;
     const double *Ui = U + (size_t)inst * N * NU;
     double *wsk = ws + (size_t)li * L::instance_stride(N) + (size_t)k * L::STAGE;
@@ -53,13 +55,14 @@ __global__ void __launch_bounds__(128) linearize_kernel(const __grid_constant__ 
 // NSLOT = 2 / MINB = 1: latency variant (stage prefetch, all the registers it wants);
 // NSLOT = 1 / MINB = 12: throughput variant the host scheduler picks for chunks of many waves
 // (16 KB of shared memory and <= 168 registers per warp -> 12 warps per SM instead of 9).
-template <int NX, int NU, int WPB, int NSLOT, int MINB>
+// STRICT: reference-semantics instantiation (mpcb_config.strict_reference, see qp_solve_warp).
+template <int NX, int NU, int WPB, int NSLOT, int MINB, bool STRICT>
 __global__ void __launch_bounds__(32 * WPB, MINB) qp_kernel(const __grid_constant__ Params P, double *__restrict__ X,
                                                       double *__restrict__ U, const double *__restrict__ x0,
                                                       const double *__restrict__ yref, int yref_mode,
                                                       double *__restrict__ ws, double *__restrict__ u0,
                                                       int32_t *__restrict__ status, int32_t *__restrict__ iters,
-                                                      int inst0, int B)
+                                                      int inst0, int B, const int32_t *__restrict__ skip)
 {
     using L = Layout<NX, NU>;
     __shared__ __align__(16) QpSmem<NX, NU, double, NSLOT> sm_arr[WPB];
@@ -68,14 +71,15 @@ __global__ void __launch_bounds__(32 * WPB, MINB) qp_kernel(const __grid_constan
     const int li = blockIdx.x * WPB + (threadIdx.x >> 5);
     if (li >= B) return;
     const int inst = inst0 + li;
+    if (skip && skip[inst]) return;  // SQP: this instance has converged
     double *Xi = X + (size_t)inst * (N + 1) * NX;
     double *Ui = U + (size_t)inst * N * NU;
     const double *yr = yref;
     if (yref_mode == MPCB_PER_INSTANCE) yr = yref + (size_t)inst * (NX + NU);
     if (yref_mode == MPCB_PER_STAGE) yr = yref + (size_t)inst * (N + 1) * (NX + NU);
     int it = 0;
-    const int st = qp_solve_warp<NX, NU, double, NSLOT>(P, *sm, ws + (size_t)li * L::instance_stride(N), Xi, Ui,
-                                                 x0 + (size_t)inst * NX, yr, yref_mode == MPCB_PER_STAGE, &it);
+    const int st = qp_solve_warp<NX, NU, double, NSLOT, STRICT>(P, *sm, ws + (size_t)li * L::instance_stride(N), Xi, Ui,
+                                                         x0 + (size_t)inst * NX, yr, yref_mode == MPCB_PER_STAGE, &it);
     const int lane = threadIdx.x & 31;
     if (lane == 0) {
         if (status) status[inst] = st;
@@ -91,14 +95,15 @@ template <int NX, int NU>
 __global__ void __launch_bounds__(32) qp8_kernel(const __grid_constant__ Params P, double *__restrict__ X, double *__restrict__ U,
                                                  const double *__restrict__ x0, const double *__restrict__ yref, int yref_mode,
                                                  double *__restrict__ ws, double *__restrict__ u0, int32_t *__restrict__ status,
-                                                 int32_t *__restrict__ iters, int inst0, int B, unsigned *__restrict__ next)
+                                                 int32_t *__restrict__ iters, int inst0, int B, unsigned *__restrict__ next,
+                                                 const int32_t *__restrict__ skip)
 {
     __shared__ Qp8Smem<NX, NU> sm;
     Qp8Batch job;
     job.X = X; job.U = U; job.x0 = x0; job.yref = yref;
     job.yref_stride = yref_mode == MPCB_PER_INSTANCE ? (size_t)(NX + NU) : yref_mode == MPCB_PER_STAGE ? (size_t)(P.N + 1) * (NX + NU) : 0;
     job.yps = yref_mode == MPCB_PER_STAGE;
-    job.ws = ws; job.u0 = u0; job.status = status; job.iters = iters; job.inst0 = inst0; job.B = B; job.next = next;
+    job.ws = ws; job.u0 = u0; job.status = status; job.iters = iters; job.inst0 = inst0; job.B = B; job.next = next; job.skip = skip;
     qp8_solve_queue<NX, NU>(P, sm, job);
 }
 
@@ -178,6 +183,149 @@ __global__ void debug_copy_kernel(const __grid_constant__ Params P, const double
     const size_t inst = (size_t)inst0 + li;
     if (e < L::NZ * NX) BAt[(inst * N + k) * (L::NZ * NX) + e] = wk[L::O_BAT + (e / NX) * L::LDB + e % NX];
     else b[(inst * N + k) * NX + (e - L::NZ * NX)] = wk[L::O_B + e - L::NZ * NX];
+}
+
+// Test hook: the interior-point iterate the last solve ended with and the QP it solved, read out of the workspace
+// records (nothing is recomputed).  One thread per (instance, stage, component); any output may be null.
+struct QpDebugOut {
+    double *z, *pi, *tl, *tu, *ll, *lu, *lb, *ub, *g;  // [B,N+1,nz] each, pi [B,N+1,nx]
+};
+template <int NX, int NU>
+__global__ void debug_qp_kernel(const __grid_constant__ Params P, const double *__restrict__ ws, QpDebugOut o, int inst0, int B)
+{
+    using L = Layout<NX, NU>;
+    const int N = P.N;
+    const size_t per = (size_t)(N + 1) * L::NZ;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= per * B) return;
+    const int li = (int)(tid / per);
+    const int k = (int)((tid % per) / L::NZ), j = (int)(tid % L::NZ);
+    const double *wk = ws + (size_t)li * L::instance_stride(N) + (size_t)k * L::STAGE;
+    const size_t inst = (size_t)inst0 + li;
+    const size_t oz = (inst * (N + 1) + k) * L::NZ + j;
+    const VarKind vk = var_kind<NX, NU>(k, j, N);
+    if (o.z) o.z[oz] = (vk.var || (k == 0 && j >= NU)) ? wk[L::O_Z + j] : 0.0;
+    if (o.tl) o.tl[oz] = vk.hasb ? wk[L::O_TL + j] : 0.0;
+    if (o.tu) o.tu[oz] = vk.hasb ? wk[L::O_TU + j] : 0.0;
+    if (o.ll) o.ll[oz] = vk.hasb ? wk[L::O_LL + j] : 0.0;
+    if (o.lu) o.lu[oz] = vk.hasb ? wk[L::O_LUP + j] : 0.0;
+    if (o.lb) o.lb[oz] = vk.hasb ? wk[L::O_LB + j] : -HUGE_VAL;
+    if (o.ub) o.ub[oz] = vk.hasb ? wk[L::O_UB + j] : HUGE_VAL;
+    if (o.g) o.g[oz] = (vk.var || (k == 0 && j >= NU)) ? wk[L::O_G + j] : 0.0;
+    if (o.pi && j < NX) o.pi[(inst * (N + 1) + k) * NX + j] = k >= 1 ? wk[L::O_PI + j] : 0.0;
+}
+
+// ---- SQP to convergence (reference options nlp_solver_max_iter / nlp_solver_tol_*,
+// acados_ocp_blasterModel.json solver_options).  Per-instance state of one mpcb_solve_sqp call:
+struct SqpState {
+    double *pi, *ll, *lu;  // multipliers of the last QP: pi[B,N+1,nx], ll / lu[B,N+1,nz]
+    int32_t *done;         // 1 once the instance has converged or failed; its iterate is then left alone
+    int32_t *status;       // SQP status: 0 converged, 2 iteration cap, 4 QP failure, 1 NaN
+    int32_t *sqp_iters;    // QP solves performed
+    int32_t *qp_iters;     // interior-point iterations over all of them
+    double *res;           // [B,4] last evaluated residuals (stat, eq, ineq, comp); may be null
+    double tol[4];
+};
+
+// NLP residuals at the stored iterate with the multipliers of the last QP, one warp per instance, right after the
+// rollout kernel has re-linearised (BAt, b in the records are those of this iterate): inf-norms of the Lagrangian
+// gradient (Gauss-Newton LINEAR_LS cost, x_0 pinned), the dynamics defect (and x_0 - X_0), the bound violation and the
+// complementarity products.  Converged instances are flagged done (and u0 is written for them).
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) nlp_res_kernel(const __grid_constant__ Params P, const double *__restrict__ X,
+                                                      const double *__restrict__ U, const double *__restrict__ x0,
+                                                      const double *__restrict__ yref, int yref_mode, const double *__restrict__ ws,
+                                                      SqpState st, int sqp_it, double *__restrict__ u0, int inst0, int B)
+{
+    using L = Layout<NX, NU>;
+    constexpr int NZ = L::NZ;
+    const int N = P.N;
+    const int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (li >= B) return;
+    const int inst = inst0 + li, lane = threadIdx.x & 31;
+    if (st.done[inst]) return;
+    const double *Xi = X + (size_t)inst * (N + 1) * NX, *Ui = U + (size_t)inst * N * NU;
+    const double *yr0 = yref;
+    if (yref_mode == MPCB_PER_INSTANCE) yr0 = yref + (size_t)inst * NZ;
+    if (yref_mode == MPCB_PER_STAGE) yr0 = yref + (size_t)inst * (N + 1) * NZ;
+    const double *pi = st.pi + (size_t)inst * (N + 1) * NX;
+    const double *ll = st.ll + (size_t)inst * (N + 1) * NZ, *lu = st.lu + (size_t)inst * (N + 1) * NZ;
+    double rs = 0.0, re = 0.0, ri = 0.0, rc = 0.0;
+    for (int k = 0; k <= N; k++) {
+        const double *wk = ws + (size_t)li * L::instance_stride(N) + (size_t)k * L::STAGE;
+        const double *yr = yr0 + (yref_mode == MPCB_PER_STAGE ? (size_t)k * NZ : 0);
+        const VarKind vk = var_kind<NX, NU>(k, lane, N);
+        if (lane < NZ) {
+            const double H0 = hess_diag<NX, NU, double>(P, k, lane);
+            double y = 0.0, yv = 0.0, lb = 0.0, ub = 0.0;
+            if (lane < NU) {
+                if (k < N) { y = Ui[(size_t)k * NU + lane]; yv = yr[NX + lane]; lb = P.lbu[lane]; ub = P.ubu[lane]; }
+            } else {
+                y = Xi[(size_t)k * NX + lane - NU]; yv = yr[lane - NU]; lb = P.lbx[lane - NU]; ub = P.ubx[lane - NU];
+            }
+            if (vk.var) {
+                double r = H0 * (y - yv);
+                if (k < N)
+                    for (int c = 0; c < NX; c++) r += wk[L::O_BAT + lane * L::LDB + c] * pi[(size_t)(k + 1) * NX + c];
+                if (lane >= NU) r -= pi[(size_t)k * NX + lane - NU];
+                if (vk.hasb) r += lu[(size_t)k * NZ + lane] - ll[(size_t)k * NZ + lane];
+                rs = fmax(rs, fabs(r));
+            }
+            if (vk.hasb) {
+                ri = fmax(ri, fmax(lb - y, y - ub));
+                rc = fmax(rc, fmax(fabs(ll[(size_t)k * NZ + lane] * (y - lb)), fabs(lu[(size_t)k * NZ + lane] * (ub - y))));
+            }
+        }
+        if (lane < NX) {
+            if (k < N) re = fmax(re, fabs(wk[L::O_B + lane]));
+            if (k == 0) re = fmax(re, fabs(x0[(size_t)inst * NX + lane] - Xi[lane]));
+        }
+    }
+    rs = warp_max(rs); re = warp_max(re); ri = warp_max(ri); rc = warp_max(rc);
+    const bool nan = !(rs == rs) || !(re == re);
+    const bool conv = !nan && rs <= st.tol[0] && re <= st.tol[1] && ri <= st.tol[2] && rc <= st.tol[3];
+    if (lane == 0) {
+        if (st.res) { double *o = st.res + (size_t)inst * 4; o[0] = rs; o[1] = re; o[2] = ri; o[3] = rc; }
+        if (conv) { st.done[inst] = 1; st.status[inst] = ST_OK; }
+        else if (nan) { st.done[inst] = 1; st.status[inst] = ST_NAN; }
+    }
+    if ((conv || nan) && u0 && lane < NU) u0[(size_t)inst * NU + lane] = Ui[lane];
+}
+
+// After the QP kernel of an SQP iteration: keep the multipliers for the next residual evaluation and account for the
+// solve.  A QP that failed leaves the iterate untouched (or, with strict_reference, only the iteration cap still applies
+// the step), so repeating it would change nothing: the instance ends with the QP-failure status, as acados' SQP does.
+template <int NX, int NU>
+__global__ void sqp_book_kernel(const __grid_constant__ Params P, const double *__restrict__ ws, SqpState st,
+                                const int32_t *__restrict__ qp_status, const int32_t *__restrict__ qp_iters, int inst0, int B)
+{
+    using L = Layout<NX, NU>;
+    const int N = P.N;
+    const size_t per = (size_t)(N + 1) * L::NZ;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= per * B) return;
+    const int li = (int)(tid / per);
+    const int k = (int)((tid % per) / L::NZ), j = (int)(tid % L::NZ);
+    const size_t inst = (size_t)inst0 + li;
+    if (st.done[inst]) return;  // flagged before this QP (the failure flag below is set by this kernel: racing readers only skip a dead copy)
+    const double *wk = ws + (size_t)li * L::instance_stride(N) + (size_t)k * L::STAGE;
+    const VarKind vk = var_kind<NX, NU>(k, j, N);
+    st.ll[(inst * (N + 1) + k) * L::NZ + j] = vk.hasb ? wk[L::O_LL + j] : 0.0;
+    st.lu[(inst * (N + 1) + k) * L::NZ + j] = vk.hasb ? wk[L::O_LUP + j] : 0.0;
+    if (j < NX) st.pi[(inst * (N + 1) + k) * NX + j] = k >= 1 ? wk[L::O_PI + j] : 0.0;
+    if (k == 0 && j == 0) {
+        const int q = qp_status[inst];
+        st.sqp_iters[inst] += 1;
+        st.qp_iters[inst] += qp_iters[inst];
+        const bool applied = q == ST_OK || (P.strict && q == ST_MAXITER);
+        if (!applied) { st.status[inst] = q == ST_NAN ? ST_NAN : ST_QPFAIL; __threadfence(); st.done[inst] = 1; }
+    }
+}
+
+__global__ void fill_i32_kernel(int32_t *a, int32_t v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
 }
 
 // Horizon shift of the stored iterate (the usual RTI companion; the reference's
@@ -291,7 +439,24 @@ struct mpcb_handle {
     unsigned *qp8_next = nullptr;    // its work counter
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // around K1 and K2 of the last solve (profiling)
     bool profile = false;
+    // state of mpcb_solve_sqp (allocated on first use): multipliers of the last QP and per-instance flags
+    double *sqp_pi = nullptr, *sqp_ll = nullptr, *sqp_lu = nullptr;
+    int32_t *sqp_done = nullptr, *sqp_status = nullptr, *sqp_count = nullptr, *sqp_qpit = nullptr;
+    int last_solve_batch = 0;  // instances whose records the workspace still holds (mpcb_debug_qp)
     std::string err;
+};
+
+// Entry points that must run on the handle's GPU make it current for their duration and restore the caller's device
+// on every return path (a process driving several GPUs keeps its own current device).
+struct DeviceGuard {
+    int prev = -1, dev;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int d) : dev(d)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
 };
 
 namespace {
@@ -342,6 +507,7 @@ Params make_params(const mpcb_config &c)
     P.ipm_max_iter = c.ipm_max_iter; P.ipm_mu0 = c.ipm_mu0; P.ipm_thr0 = c.ipm_thr0;
     P.tol_stat = c.tol_stat; P.tol_eq = c.tol_eq; P.tol_ineq = c.tol_ineq; P.tol_comp = c.tol_comp;
     P.alpha_min = c.alpha_min;
+    P.strict = c.strict_reference ? 1 : 0;
     return P;
 }
 
@@ -352,34 +518,54 @@ constexpr int kWPB = 1;  // warps (= instances) per CTA of the QP kernel
 
 template <int NX, int NU>
 int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
-                        double *u0, int32_t *status, int32_t *iters, int B, cudaStream_t s)
+                        double *u0, int32_t *status, int32_t *iters, int B, cudaStream_t s, const SqpState *sqp = nullptr,
+                        int sqp_it = 0, bool sqp_eval_only = false)
 {
     static_assert(sizeof(QpSmem<NX, NU, double, 2>) * kWPB <= 48 * 1024, "static shared memory limit");
+    using L = Layout<NX, NU>;
     const size_t smem = 0;
+    const int32_t *skip = sqp ? sqp->done : nullptr;
     for (int i0 = 0; i0 < B; i0 += h->ws_batch) {
         const int nb = (B - i0 < h->ws_batch) ? B - i0 : h->ws_batch;
         const long long warps = (long long)nb * h->N;
         const unsigned g1 = (unsigned)((warps * 32 + 127) / 128);
         const bool prof = h->profile && i0 == 0;
         if (prof) cudaEventRecord(h->ev[0], s);
-        linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+        linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb, skip);
+        g_launches += 1;
+        if (sqp) {
+            nlp_res_kernel<NX, NU><<<(unsigned)(((long long)nb * 32 + 127) / 128), 128, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, *sqp,
+                                                                                             sqp_it, u0, i0, nb);
+            g_launches += 1;
+            if (sqp_eval_only) continue;
+        }
         if (prof) cudaEventRecord(h->ev[1], s);
-        if (nb >= h->qp8_batch) {
+        if (h->P.strict)
+            // reference semantics (explicit residual norms, no divergence exit): the one-instance latency kernel, any batch
+            qp_kernel<NX, NU, kWPB, 2, 1, true><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+                                                                                                  h->ws, u0, status, iters, i0, nb, skip);
+        else if (nb >= h->qp8_batch) {
             // one wave of resident warps; their groups draw the chunk's instances from the work counter
             const int want = (nb + kGPW - 1) / kGPW;
             const int grid = want < h->qp8_resident ? want : h->qp8_resident;
             CK(h, cudaMemsetAsync(h->qp8_next, 0, sizeof(unsigned), s));
-            qp8_kernel<NX, NU><<<grid, 32, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb, h->qp8_next);
+            qp8_kernel<NX, NU><<<grid, 32, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb, h->qp8_next, skip);
         }
         else if (nb >= h->throughput_batch)
-            qp_kernel<NX, NU, kWPB, 1, MPCB_TP_MINB><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
-                                                                                             h->ws, u0, status, iters, i0, nb);
+            qp_kernel<NX, NU, kWPB, 1, MPCB_TP_MINB, false><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+                                                                                                    h->ws, u0, status, iters, i0, nb, skip);
         else
-            qp_kernel<NX, NU, kWPB, 2, 1><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
-                                                                                            h->ws, u0, status, iters, i0, nb);
+            qp_kernel<NX, NU, kWPB, 2, 1, false><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+                                                                                                   h->ws, u0, status, iters, i0, nb, skip);
         if (prof) cudaEventRecord(h->ev[2], s);
-        g_launches += 2;
+        g_launches += 1;
+        if (sqp) {
+            const size_t per = (size_t)(h->N + 1) * L::NZ;
+            sqp_book_kernel<NX, NU><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, *sqp, status, iters, i0, nb);
+            g_launches += 1;
+        }
     }
+    h->last_solve_batch = B <= h->ws_batch ? B : 0;
     CK(h, cudaGetLastError());
     return 0;
 }
@@ -416,6 +602,7 @@ int mpcb_config_default(mpcb_config *cfg, int variant, int N)
     cfg->ipm_max_iter = 60; cfg->ipm_mu0 = 1e2; cfg->ipm_thr0 = -0.5;
     cfg->tol_stat = 1e-6; cfg->tol_eq = 1e-8; cfg->tol_ineq = 1e-8; cfg->tol_comp = 1e-8; cfg->alpha_min = 1e-8;
     cfg->dtype = MPCB_F64; cfg->max_batch = 1024; cfg->ws_batch = 0; cfg->device = -1;
+    cfg->strict_reference = 0; cfg->throughput_batch = 0; cfg->qp8_batch = 0; cfg->qp8_warps = 0;
     if (variant == 13) {
         // QUAT13: x = [p, q(w,x,y,z), v, omega].  The Euler weights go to the quaternion components; the Euler boxes
         // (10, 10, 20 deg) become boxes on the vector part (sine of half the angle), q_w stays near 1.
@@ -469,8 +656,8 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     } else {
         cudaGetDevice(&h->device);
     }
-    e = cudaSetDevice(h->device);
-    if (e != cudaSuccess) { fail(nullptr, "cudaSetDevice", e); delete h; return -1; }
+    DeviceGuard guard(h->device);  // the caller's current device is restored on every return path
+    if (guard.err != cudaSuccess) { fail(nullptr, "cudaSetDevice", guard.err); delete h; return -1; }
     h->ws_stride = cfg->variant == 17 ? Layout<17, 6>::instance_stride(h->N)
                    : cfg->variant == 13 ? Layout<13, 4>::instance_stride(h->N) : Layout<12, 4>::instance_stride(h->N);
     int wsb = cfg->ws_batch;
@@ -484,17 +671,16 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     if (wsb > h->max_batch) wsb = h->max_batch;
     h->ws_batch = wsb;
     {
-        // more than ~2 waves of the latency variant (9 warps x 148 SMs): switch to the throughput variant
-        const char *tb = getenv("MPCB_THROUGHPUT_BATCH");
-        h->throughput_batch = tb ? atoi(tb) : 4096;
-        // four-instances-per-warp kernel (persistent, groups refilled from a work counter, next stage's record
-        // prefetched into L2): measured faster than the one-instance kernel from ~2,600 instances on for QUAD12
-        // (576 k against 487 k solves/s at 3,072; 1.00 M against 621 k at 65,536) and from two of its waves
-        // (148 SMs x 7 warps x 4 = 4,144 instances each) on for BLASTER17 (390 k against 362 k at 8,192; 378 k
-        // against 374 k at 10,240; 424 k against 383 k at 16,384; 460 k against 393 k at 65,536).
-        // MPCB_QP8_BATCH=<chunk size> overrides the threshold.
-        const char *q8 = getenv("MPCB_QP8_BATCH");
-        h->qp8_batch = q8 ? atoi(q8) : (cfg->variant == 17 ? 8192 : 3072);
+        // Kernel selection by chunk size (mpcb_config fields; 0 = the measured defaults):
+        //  * throughput_batch: from ~2 waves of the latency variant (9 warps x 148 SMs) on, the single-buffer variant
+        //    (12 warps per SM) wins -- re-measured in round 2 with the hybrid factorisation in the latency variant:
+        //    331 k against 307 k solves/s at 4,096 BLASTER17 instances, 351 k against 307 k at 6,144;
+        //  * qp8_batch: the four-instances-per-warp kernel (persistent, groups refilled from a work counter, next
+        //    stage's record prefetched into L2) is faster from ~2,600 instances on for QUAD12 (576 k against 487 k
+        //    solves/s at 3,072) and from two of its waves (148 SMs x 7 warps x 4 = 4,144 instances each) on for
+        //    BLASTER17 (390 k against 362 k at 8,192; 460 k against 393 k at 65,536).
+        h->throughput_batch = cfg->throughput_batch > 0 ? cfg->throughput_batch : 4096;
+        h->qp8_batch = cfg->qp8_batch > 0 ? cfg->qp8_batch : (cfg->variant == 17 ? 8192 : 3072);
     }
     const size_t B = (size_t)h->max_batch;
     const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;
@@ -523,8 +709,7 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
         if (e != cudaSuccess || per_sm < 1 || sms < 1) { fail(nullptr, "occupancy query of qp8_kernel", e); mpcb_destroy(h); return -1; }
         h->qp8_resident = per_sm * sms;
         // test hook: a smaller grid makes the groups of a warp go through many instances
-        const char *qw = getenv("MPCB_QP8_WARPS");
-        if (qw && atoi(qw) >= 1 && atoi(qw) < h->qp8_resident) h->qp8_resident = atoi(qw);
+        if (cfg->qp8_warps >= 1 && cfg->qp8_warps < h->qp8_resident) h->qp8_resident = cfg->qp8_warps;
     }
     double pd[kNP] = {0};
     pd[24] = 2.2 * 9.81;  // reference blastermodel.py:280-282
@@ -547,7 +732,9 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
 int mpcb_destroy(mpcb_handle *h)
 {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
+    cudaFree(h->sqp_pi); cudaFree(h->sqp_ll); cudaFree(h->sqp_lu);
+    cudaFree(h->sqp_done); cudaFree(h->sqp_status); cudaFree(h->sqp_count); cudaFree(h->sqp_qpit);
     cudaFree(h->X); cudaFree(h->U); cudaFree(h->ws); cudaFree(h->p_default);
     cudaFree(h->status_scratch); cudaFree(h->iters_scratch); cudaFree(h->xn_scratch); cudaFree(h->u0_scratch);
     cudaFree(h->d_stage); cudaFree(h->qp8_next);
@@ -604,7 +791,8 @@ int mpcb_solve_host(mpcb_handle *h, const double *x0, const double *yref, int yr
     if (!x0 || !yref) return fail(h, "x0 and yref are required");
     if (yref_mode < 0 || yref_mode > 2 || p_mode < 0 || p_mode > 2) return fail(h, "bad yref_mode / p_mode");
     if (B == 0) return 0;
-    CK(h, cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
+    if (guard.err != cudaSuccess) return fail(h, "cudaSetDevice", guard.err);
     const int nx = h->nx, nu = h->nu, N = h->N, ny = nx + nu;
     const size_t n_x0 = (size_t)B * nx;
     const size_t n_y = yref_mode == MPCB_SHARED ? ny : yref_mode == MPCB_PER_INSTANCE ? (size_t)B * ny : (size_t)B * (N + 1) * ny;
@@ -734,20 +922,21 @@ int mpcb_debug_linearize(mpcb_handle *h, const double *p, int p_mode, double *BA
         const long long warps = (long long)nb * h->N;
         const unsigned g1 = (unsigned)((warps * 32 + 127) / 128);
         if (h->nx == 17) {
-            linearize_kernel<17, 6><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+            linearize_kernel<17, 6><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb, nullptr);
             const size_t per = (size_t)h->N * (23 * 17 + 17);
             debug_copy_kernel<17, 6><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, BAt, b, i0, nb);
         } else if (h->nx == 13) {
-            linearize_kernel<13, 4><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+            linearize_kernel<13, 4><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb, nullptr);
             const size_t per = (size_t)h->N * (17 * 13 + 13);
             debug_copy_kernel<13, 4><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, BAt, b, i0, nb);
         } else {
-            linearize_kernel<12, 4><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb);
+            linearize_kernel<12, 4><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb, nullptr);
             const size_t per = (size_t)h->N * (16 * 12 + 12);
             debug_copy_kernel<12, 4><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, BAt, b, i0, nb);
         }
         g_launches += 2;
     }
+    h->last_solve_batch = 0;  // the records no longer belong to the last solve
     CK(h, cudaGetLastError());
     return 0;
 }
@@ -765,15 +954,109 @@ int mpcb_shift(mpcb_handle *h, int B, void *stream)
     return 0;
 }
 
-int mpcb_solve_sqp(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
-                   int sqp_iters, double *u0, double *X, double *U, int32_t *status, int32_t *iters, int B, void *stream)
+namespace {
+int sqp_alloc(mpcb_handle *h)
 {
-    if (sqp_iters < 1) return fail(h, "sqp_iters must be >= 1");
-    for (int it = 0; it < sqp_iters; it++) {
-        const bool last = it + 1 == sqp_iters;
-        if (mpcb_solve(h, x0, yref, yref_mode, p, p_mode, u0, last ? X : nullptr, last ? U : nullptr, status, iters, B, stream))
-            return -1;
+    if (h->sqp_done) return 0;
+    const size_t B = (size_t)h->max_batch, s1 = (size_t)(h->N + 1);
+    CK(h, cudaMalloc((void **)&h->sqp_pi, B * s1 * h->nx * sizeof(double)));
+    CK(h, cudaMalloc((void **)&h->sqp_ll, B * s1 * (h->nx + h->nu) * sizeof(double)));
+    CK(h, cudaMalloc((void **)&h->sqp_lu, B * s1 * (h->nx + h->nu) * sizeof(double)));
+    CK(h, cudaMalloc((void **)&h->sqp_done, B * sizeof(int32_t)));
+    CK(h, cudaMalloc((void **)&h->sqp_status, B * sizeof(int32_t)));
+    CK(h, cudaMalloc((void **)&h->sqp_count, B * sizeof(int32_t)));
+    CK(h, cudaMalloc((void **)&h->sqp_qpit, B * sizeof(int32_t)));
+    return 0;
+}
+}  // namespace
+
+int mpcb_solve_sqp(mpcb_handle *h, const double *x0, const double *yref, int yref_mode, const double *p, int p_mode,
+                   int max_iter, const double *tol, double *u0, double *X, double *U, int32_t *status, int32_t *iters,
+                   int32_t *sqp_iters, double *nlp_res, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (max_iter < 1) return fail(h, "max_iter must be >= 1");
+    if (!x0 || !yref) return fail(h, "x0 and yref are required");
+    if (yref_mode < 0 || yref_mode > 2 || p_mode < 0 || p_mode > 2) return fail(h, "bad yref_mode / p_mode");
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!tol) {
+        // fixed number of SQP iterations, no residual test: status / iters are those of the last QP
+        for (int it = 0; it < max_iter; it++) {
+            const bool last = it + 1 == max_iter;
+            if (mpcb_solve(h, x0, yref, yref_mode, p, p_mode, u0, last ? X : nullptr, last ? U : nullptr, status, iters, B, stream))
+                return -1;
+        }
+        if (sqp_iters) { fill_i32_kernel<<<(B + 255) / 256, 256, 0, s>>>(sqp_iters, max_iter, B); g_launches += 1; }
+        if (nlp_res) CK(h, cudaMemsetAsync(nlp_res, 0, (size_t)B * 4 * sizeof(double), s));
+        CK(h, cudaGetLastError());
+        return 0;
     }
+    for (int i = 0; i < 4; i++)
+        if (!(tol[i] >= 0)) return fail(h, "SQP tolerances must be non-negative");
+    if (sqp_alloc(h)) return -1;
+    if (!p) { p = h->p_default; p_mode = MPCB_SHARED; }
+    const size_t s1 = (size_t)(h->N + 1);
+    SqpState st;
+    st.pi = h->sqp_pi; st.ll = h->sqp_ll; st.lu = h->sqp_lu;
+    st.done = h->sqp_done; st.status = h->sqp_status; st.sqp_iters = h->sqp_count; st.qp_iters = h->sqp_qpit; st.res = nlp_res;
+    for (int i = 0; i < 4; i++) st.tol[i] = tol[i];
+    // acados' default initial multipliers are zero [upstream D4]
+    CK(h, cudaMemsetAsync(st.pi, 0, (size_t)B * s1 * h->nx * sizeof(double), s));
+    CK(h, cudaMemsetAsync(st.ll, 0, (size_t)B * s1 * (h->nx + h->nu) * sizeof(double), s));
+    CK(h, cudaMemsetAsync(st.lu, 0, (size_t)B * s1 * (h->nx + h->nu) * sizeof(double), s));
+    CK(h, cudaMemsetAsync(st.done, 0, (size_t)B * sizeof(int32_t), s));
+    CK(h, cudaMemsetAsync(st.sqp_iters, 0, (size_t)B * sizeof(int32_t), s));
+    CK(h, cudaMemsetAsync(st.qp_iters, 0, (size_t)B * sizeof(int32_t), s));
+    fill_i32_kernel<<<(B + 255) / 256, 256, 0, s>>>(st.status, ST_MAXITER, B);
+    g_launches += 1;
+    // acados' SQP loop: linearise, evaluate the residuals, stop if converged, else solve the QP and take the full step;
+    // after max_iter QPs the status is max-iter (one more linearisation reports the residuals of the final iterate).
+    for (int it = 0; it <= max_iter; it++) {
+        const bool eval_only = it == max_iter;
+        int rc = (h->nx == 17)   ? launch_solve_chunks<17, 6>(h, x0, yref, yref_mode, p, p_mode, h->u0_scratch, h->status_scratch, h->iters_scratch, B, s, &st, it, eval_only)
+                 : (h->nx == 13) ? launch_solve_chunks<13, 4>(h, x0, yref, yref_mode, p, p_mode, h->u0_scratch, h->status_scratch, h->iters_scratch, B, s, &st, it, eval_only)
+                                 : launch_solve_chunks<12, 4>(h, x0, yref, yref_mode, p, p_mode, h->u0_scratch, h->status_scratch, h->iters_scratch, B, s, &st, it, eval_only);
+        if (rc) return rc;
+    }
+    h->last_solve_batch = 0;
+    const size_t nu = h->nu;
+    if (u0) CK(h, cudaMemcpyAsync(u0, h->u0_scratch, (size_t)B * nu * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (status) CK(h, cudaMemcpyAsync(status, st.status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (iters) CK(h, cudaMemcpyAsync(iters, st.qp_iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (sqp_iters) CK(h, cudaMemcpyAsync(sqp_iters, st.sqp_iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (X) CK(h, cudaMemcpyAsync(X, h->X, (size_t)B * (h->N + 1) * h->nx * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (U) CK(h, cudaMemcpyAsync(U, h->U, (size_t)B * h->N * h->nu * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int mpcb_debug_qp(mpcb_handle *h, double *z, double *pi, double *tl, double *tu, double *ll, double *lu, double *lb, double *ub,
+                  double *g, double *BAt, double *b, int B, void *stream)
+{
+    if (check_batch(h, B)) return -1;
+    if (B == 0) return 0;
+    if (B > h->last_solve_batch)
+        return fail(h, "mpcb_debug_qp: the workspace does not hold the records of that many instances of the last mpcb_solve "
+                       "(call it right after a solve of at most ws_batch instances)");
+    cudaStream_t s = (cudaStream_t)stream;
+    QpDebugOut o{z, pi, tl, tu, ll, lu, lb, ub, g};
+    const int nz = h->nx + h->nu;
+    const size_t per = (size_t)(h->N + 1) * nz;
+    const unsigned grid = (unsigned)((per * B + 255) / 256);
+    const size_t per2 = (size_t)h->N * ((size_t)nz * h->nx + h->nx);
+    const unsigned grid2 = (unsigned)((per2 * B + 255) / 256);
+    if (h->nx == 17) {
+        debug_qp_kernel<17, 6><<<grid, 256, 0, s>>>(h->P, h->ws, o, 0, B);
+        if (BAt && b) debug_copy_kernel<17, 6><<<grid2, 256, 0, s>>>(h->P, h->ws, BAt, b, 0, B);
+    } else if (h->nx == 13) {
+        debug_qp_kernel<13, 4><<<grid, 256, 0, s>>>(h->P, h->ws, o, 0, B);
+        if (BAt && b) debug_copy_kernel<13, 4><<<grid2, 256, 0, s>>>(h->P, h->ws, BAt, b, 0, B);
+    } else {
+        debug_qp_kernel<12, 4><<<grid, 256, 0, s>>>(h->P, h->ws, o, 0, B);
+        if (BAt && b) debug_copy_kernel<12, 4><<<grid2, 256, 0, s>>>(h->P, h->ws, BAt, b, 0, B);
+    }
+    g_launches += 2;
+    CK(h, cudaGetLastError());
     return 0;
 }
 
@@ -796,10 +1079,12 @@ int mpcb_last_kernel_ms(mpcb_handle *h, float *ms_linearize, float *ms_qp)
 int mpcb_fp64_peak(int device, double *tflops)
 {
     if (!tflops) return -1;
-    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return -1;
-    cudaDeviceProp prop;
     int dev = 0;
-    cudaGetDevice(&dev);
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    DeviceGuard guard(device >= 0 ? device : dev);
+    if (guard.err != cudaSuccess) return -1;
+    if (device >= 0) dev = device;
+    cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
     double *out = nullptr;

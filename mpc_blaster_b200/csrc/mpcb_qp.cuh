@@ -31,7 +31,7 @@ namespace mpcb {
 // Also only while mu <= mu0: on an infeasible QP the multipliers diverge (mu climbs towards the 100 * mu0 exit) and the Gram
 // matrix loses a pivot before the LQ does -- the instance would end with ST_QPFAIL where the checkers report ST_MINSTEP.
 #ifndef MPCB_GRAM_MU
-#define MPCB_GRAM_MU 1e-4
+#define MPCB_GRAM_MU 1e-5
 #endif
 constexpr double kMuDiverge = 1e2;  // infeasibility test: mu > kMuDiverge * mu0 (the CPU checkers apply the same test; no feasible instance of the test scenarios exceeds 3 * mu0)
 
@@ -173,6 +173,43 @@ MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
         if (lane > c && lane < nz) out -= Lu[c] * lc;
     }
     return out;
+}
+
+// Explicit max-norms of the dynamics residual r_k = b_k + [B A] z_k - dx_{k+1} and of the bound-slack residuals
+// z - lb - t_l, ub - z - t_u at the current QP iterate: one flat pass over the records (independent loads, nothing
+// serial).  The stopping test tracks these two through their exact-arithmetic decay (1 - alpha) per iteration; this
+// pass is run once, when that test is about to report success, so that ST_OK is never decided on extrapolated
+// values alone (the stationarity norm stays extrapolated: DESIGN.md section 2.5).
+template <int NX, int NU, typename T>
+MPCB_DEV void explicit_residuals(const T *__restrict__ ws, int N, T &res_b, T &res_d)
+{
+    using L = Layout<NX, NU>;
+    constexpr int NZ = L::NZ;
+    const int lane = lane_id();
+    T eb = T(0), ed = T(0);
+    MPCB_NOUNROLL
+    for (int k = 0; k <= N; k++) {
+        const T *wk = ws + (size_t)k * L::STAGE;
+        if (var_kind<NX, NU>(k, lane, N).hasb) {
+            const T z = wk[L::O_Z + lane];
+            ed = fmax(ed, fmax(fabs(z - wk[L::O_LB + lane] - wk[L::O_TL + lane]), fabs(wk[L::O_UB + lane] - z - wk[L::O_TU + lane])));
+        }
+        if (k < N && lane < NX) {
+            T a0 = wk[L::O_B + lane] - wk[L::STAGE + L::O_Z + NU + lane], a1 = T(0), a2 = T(0), a3 = T(0);
+            MPCB_UNROLL
+            for (int j = 0; j + 3 < NZ; j += 4) {
+                a0 += wk[L::O_BAT + j * L::LDB + lane] * wk[L::O_Z + j];
+                a1 += wk[L::O_BAT + (j + 1) * L::LDB + lane] * wk[L::O_Z + j + 1];
+                a2 += wk[L::O_BAT + (j + 2) * L::LDB + lane] * wk[L::O_Z + j + 2];
+                a3 += wk[L::O_BAT + (j + 3) * L::LDB + lane] * wk[L::O_Z + j + 3];
+            }
+            MPCB_UNROLL
+            for (int j = NZ & ~3; j < NZ; j++) a0 += wk[L::O_BAT + j * L::LDB + lane] * wk[L::O_Z + j];
+            eb = fmax(eb, fabs((a0 + a1) + (a2 + a3)));
+        }
+    }
+    res_b = warp_max(eb);
+    res_d = warp_max(ed);
 }
 
 // One forward sweep: dz_k = [du_k; dx_k] with du_k = -Luu^{-T}(lvec_k + Lxu' dx_k),
@@ -329,7 +366,10 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
 // The whole QP solve for one instance.  On return the persistent iterate Xi/Ui has taken
 // the full step (FIXED_STEP, step length 1.0: acados_ocp_blasterModel.json globalization /
 // nlp_solver_step_length).  Returns the status; *iters_out = IPM iterations.
-template <int NX, int NU, typename T, int NSLOT>
+// STRICT (mpcb_config.strict_reference): the stopping test uses the residual norms of the iterate evaluated explicitly
+// in the backward sweep S1 (stationarity included, as HPIPM's test does) instead of their extrapolated values, there is
+// no early exit on diverging multipliers, and the last iterate is applied when the iteration cap is reached.
+template <int NX, int NU, typename T, int NSLOT, bool STRICT = false>
 MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__restrict__ ws, T *__restrict__ Xi,
                            T *__restrict__ Ui, const T *__restrict__ x0, const T *__restrict__ yref, int yps,
                            int *iters_out)
@@ -404,13 +444,20 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
 
     for (it = 0; it < P.ipm_max_iter; it++) {
         if (!(est_g == est_g) || !(est_b == est_b) || !(mu == mu)) { status = ST_NAN; break; }
-        // diverging multipliers (mean complementarity 100 x its starting value) are the signature of
-        // an infeasible QP: stop instead of running to the iteration cap (same status as min-step)
-        if (mu > T(kMuDiverge) * mu0) { status = ST_MINSTEP; break; }
-        if (est_g <= (T)P.tol_stat && est_b <= (T)P.tol_eq && est_d <= (T)P.tol_ineq && comp <= (T)P.tol_comp) {
-            status = ST_OK;
-            break;
+        if (!STRICT) {
+            // diverging multipliers (mean complementarity 100 x its starting value) are the signature of
+            // an infeasible QP: stop instead of running to the iteration cap (same status as min-step)
+            if (mu > T(kMuDiverge) * mu0) { status = ST_MINSTEP; break; }
+            if (est_g <= (T)P.tol_stat && est_b <= (T)P.tol_eq && est_d <= (T)P.tol_ineq && comp <= (T)P.tol_comp) {
+                // est_b / est_d are extrapolations (res_0 * prod(1 - alpha)): confirm them on the iterate itself
+                T xb, xd;
+                explicit_residuals<NX, NU, T>(ws, N, xb, xd);
+                if (xb <= (T)P.tol_eq && xd <= (T)P.tol_ineq) { status = ST_OK; break; }
+                est_b = xb;
+                est_d = xd;
+            }
         }
+        T xg = T(0), xb = T(0), xd = T(0);  // STRICT: explicit residual norms of this iterate, gathered by S1
         // ================= S1: backward sweep -- residuals, factorisation, affine right-hand side
         // record k: run A = [BAt], run B = [z tl tu ll lu lb ub g pi b]
         constexpr int RUNB = L::O_C1 - L::O_Z;
@@ -430,6 +477,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 const T H0 = H0N;
                 const T zN = wN[L::O_Z + lane], piN = wN[L::O_PI + i];
                 const T q = H0 * zN + wN[L::O_G + lane] - piN;
+                if (STRICT) xg = fmax(xg, fabs(q));
                 sm.Lxx[i * NX + i] = sqrt(H0);
                 MPCB_UNROLL
                 for (int c = 0; c < NX; c++)
@@ -474,10 +522,12 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     if (NX & 1) r0 += brow[NX - 1] * sm.cPi[NX - 1];
                     q = r0 + r1;
                     if (lane >= NU) q -= s[L::O_PI + lane - NU];
+                    if (STRICT) xg = fmax(xg, fabs(q));
                 }
                 if (vk.hasb) {
                     const T itl = fast_rcp(tl), itu = fast_rcp(tu);
                     const T rdl = zj - s[L::O_LB + lane] - tl, rdu = s[L::O_UB + lane] - zj - tu;
+                    if (STRICT) xd = fmax(xd, fmax(fabs(rdl), fabs(rdu)));
                     Hd += ll * itl + lu * itu;
                     // affine right-hand side (r_m = lam*t):  q += lam_l + lam_l r_dl/t_l - lam_u - lam_u r_du/t_u
                     q += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
@@ -496,6 +546,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 MPCB_UNROLL
                 for (int j = NZ & ~3; j < NZ; j++) a0 += s[L::O_BAT + j * L::LDB + lane] * s[L::O_Z + j];
                 const T rb = (a0 + a1) + (a2 + a3);
+                if (STRICT) xb = fmax(xb, fabs(rb));
                 wk[L::O_RB + lane] = rb;
                 sm.sRb[lane] = rb;
             }
@@ -539,42 +590,6 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 T m[NZ + 1];
                 MPCB_UNROLL
                 for (int c = 0; c <= NZ; c++) m[c] = T(0);
-#ifdef MPCB_GRAM_WINDOW
-                // Experiment prepared at the end of round 1, not yet measured on a GPU (isolated in
-                // tools/ubench_gram.cu): M is symmetric, so the entries (i, (i - d) mod NZ), d = 0 .. NZ/2, over all lanes i
-                // cover every pair -- NZ/2 + 1 dot products per lane instead of NZ, in a rolled loop; the results go
-                // through a packed lower triangle (rows padded to even length) in the unused tail of the OTHER record
-                // image and every lane reads its row back.
-                {
-                    constexpr int ND = NZ / 2 + 1;
-                    auto row_off = [](int r) { return 2 * (r >> 1) * ((r >> 1) + 1) + (r & 1) * (2 * (r >> 1) + 2); };
-                    static_assert(2 * ((NZ - 1) >> 1) * (((NZ - 1) >> 1) + 1) + ((NZ - 1) & 1) * (2 * ((NZ - 1) >> 1) + 2) + L::NZP <= L::STAGE - L::O_C1,
-                                  "the packed triangle must fit the unused tail of the other record image");
-                    T *Msh = sm.slot[half ^ 1] + L::O_C1;
-                    const int ri = lane < NZ ? lane : 0;
-                    MPCB_PRAGMA_UNROLL2
-                    for (int d = 0; d < ND; d++) {
-                        int c = ri - d;
-                        if (c < 0) c += NZ;
-                        T v[NX];
-                        sp_row_load<0, NX>(sptr_add(w0, c * LDW), v);
-                        T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
-                        MPCB_UNROLL
-                        for (int i = 0; i + 3 < NX; i += 4) { d0 += v[i] * w[i]; d1 += v[i + 1] * w[i + 1]; d2 += v[i + 2] * w[i + 2]; d3 += v[i + 3] * w[i + 3]; }
-                        MPCB_UNROLL
-                        for (int i = NX & ~3; i < NX; i++) d0 += v[i] * w[i];
-                        const T val = ((d0 + d1) + (d2 + d3)) + (d == 0 ? Hd : T(0));
-                        const int rr = ri > c ? ri : c, qq = ri > c ? c : ri;
-                        if (lane < NZ) Msh[row_off(rr) + qq] = val;
-                    }
-                    warp_sync();
-                    const sptr mrow = sptr_of(Msh + row_off(ri));
-                    static_for<0, NZ, 2>([&](auto Cc) {
-                        constexpr int c = decltype(Cc)::value;
-                        sp_ld2<c>(mrow, m[c], m[c + 1]);  // entries past the row's own length belong to later rows: never used
-                    });
-                }
-#else
                 auto gram = [&](auto C) {
                     constexpr int c = decltype(C)::value;
                     T v[NX];
@@ -588,7 +603,6 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 };
                 static_for<0, NU>(gram);
                 if (k > 0) static_for<NU, NZ>(gram);
-#endif
                 const sptr cb0 = sptr_of(sm.Lcol);
                 const sptr cbl = sptr_add(cb0, lane < NZ ? lane : 0);
                 T sig = T(1);
@@ -628,12 +642,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             // NOT unrolled: its body (~2 KB of SASS) then stays in the L0 instruction cache, which
             // matters at 1-2 resident warps per scheduler.  Column j of L goes to shared memory
             // (sm.Lcol, [NZ][NZ+1]); at stage 0 only the u-block is needed (x_0 is pinned).
-#ifdef MPCB_GRAM_X
-            const bool gram_x = (NSLOT == 2) && mu > T(MPCB_GRAM_X) && mu <= (T)P.ipm_mu0;  // the x-block then follows below in normal-equations form
-            const int jend = (k == 0 || gram_x) ? NU : NZ;
-#else
             const int jend = (k == 0) ? NU : NZ;
-#endif
             T sig = T(1);
             if (lane >= NZ) {
                 MPCB_UNROLL
@@ -693,60 +702,6 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             }
             last_sig = sig;
             warp_sync();
-#ifdef MPCB_GRAM_X
-            // Experiment prepared at the end of round 1, parity-checked in the host emulator, not yet measured on a GPU
-            // (DESIGN.md section 9).  The cancellation that rules the normal equations out near the solution sits in
-            // the elimination of the INPUTS (Schur complement over the thrusts); once the
-            // NU input pivots have been done by Householder reflections, what is left for the states is
-            // diag(Hd_x) + W_x W_x' with the barrier terms on the diagonal only, which a Cholesky handles.  So: NU LQ
-            // pivots above, then Gram matrix + unrolled Cholesky on the NX state rows (lane NU + r owns row r).
-            if (k > 0 && gram_x) {
-                constexpr int LDW = (NX + 1) & ~1;
-                static_assert(NX * LDW <= L::STAGE - L::O_C1, "the W image must fit the part of the record image this sweep does not fetch");
-                static_assert(2 * L::NXP <= 2 * L::NXP, "column buffer = sm.vrow");
-                const bool xl = lane >= NU && lane < NZ;
-                const int r = xl ? lane - NU : 0;
-                T *Wsh = sm.slot[half] + L::O_C1;
-                sp_row_store<0, NX>(sptr_of(Wsh + r * LDW), w, xl);
-                warp_sync();
-                const sptr w0 = sptr_of(Wsh);
-                T m[NX + 1];
-                m[NX] = T(0);
-                static_for<0, NX>([&](auto C) {
-                    constexpr int c = decltype(C)::value;
-                    T v[NX];
-                    sp_row_load<0, NX>(sptr_add(w0, c * LDW), v);
-                    T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
-                    MPCB_UNROLL
-                    for (int i = 0; i + 3 < NX; i += 4) { d0 += v[i] * w[i]; d1 += v[i + 1] * w[i + 1]; d2 += v[i + 2] * w[i + 2]; d3 += v[i + 3] * w[i + 3]; }
-                    MPCB_UNROLL
-                    for (int i = NX & ~3; i < NX; i++) d0 += v[i] * w[i];
-                    m[c] = ((d0 + d1) + (d2 + d3)) + ((xl && r == c) ? Hd : T(0));
-                });
-                const sptr cb0 = sptr_of(sm.vrow[0]);
-                const sptr cbl = sptr_add(cb0, r);
-                static_for<0, NX>([&](auto J) {
-                    constexpr int j = decltype(J)::value;
-                    constexpr int par = (j & 1) * L::NXP;
-                    sp_st1<par>(cbl, m[j], xl);
-                    warp_sync();
-                    T a[NX + 1];
-                    static_for<(j & ~1), NX, 2>([&](auto Cc) {
-                        constexpr int c = decltype(Cc)::value;
-                        sp_ld2<par + c>(cb0, a[c], a[c + 1]);
-                    });
-                    const T rs = fast_rsqrt(a[j]);
-                    sig = a[j] * rs;
-                    const T f = m[j] * (rs * rs);
-                    const T lij = m[j] * rs;
-                    MPCB_UNROLL
-                    for (int c = j + 1; c < NX; c++) m[c] -= f * a[c];
-                    if (xl && r >= j) sm.Lxx[r * NX + j] = (r == j) ? sig : lij;
-                });
-                last_sig = sig;
-                warp_sync();
-            }
-#endif
 
             MPCB_UNROLL
             for (int c = 0; c < NU; c++) { Lu[c] = sm.Lcol[(lane < NZ ? lane : 0) * L::NUP + c]; invd[c] = sm.Linv[c]; }
@@ -775,6 +730,12 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
         }
         pipe_fence();  // L, lvec, r_b, p written by this sweep are fetched by the next ones
         warp_sync();
+        if (STRICT) {
+            // reference semantics: test the residuals S1 has just evaluated on this iterate (before using the factorisation)
+            xg = warp_max(xg); xb = warp_max(xb); xd = warp_max(xd);
+            if (!(xg == xg) || !(xb == xb)) { status = ST_NAN; break; }
+            if (xg <= (T)P.tol_stat && xb <= (T)P.tol_eq && xd <= (T)P.tol_ineq && comp <= (T)P.tol_comp) { status = ST_OK; break; }
+        }
         // a breakdown (NaN) anywhere in the recursion propagates into the last pivot of stage 0
         if (!(last_sig == last_sig) || !(last_sig < T(HUGE_VAL))) { status = ST_QPFAIL; break; }
 
@@ -903,10 +864,12 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
 
     // ---------------- RTI update: X += dx, U += du (full step).  A failed QP (status != 0: NaN,
     // max-iter, min-step = infeasible, breakdown) leaves the iterate untouched, so one bad solve
-    // cannot poison the warm start of the following control steps.
+    // cannot poison the warm start of the following control steps.  STRICT: the last iterate is
+    // applied when the iteration cap was hit, as acados does with HPIPM's max-iter return.
     warp_sync();
+    const bool take = status == ST_OK || (STRICT && status == ST_MAXITER);
     MPCB_UNROLL4
-    for (int k = 0; k <= (status == ST_OK ? N : -1); k++) {
+    for (int k = 0; k <= (take ? N : -1); k++) {
         const T *wk = ws + (size_t)k * L::STAGE;
         if (lane < NU) {
             if (k < N) Ui[(size_t)k * NU + lane] += wk[L::O_Z + lane];

@@ -333,7 +333,49 @@ struct Qp8Batch {
     int32_t *status, *iters;
     int inst0, B;
     unsigned *next;            // work counter of the chunk (zero at launch)
+    const int32_t *skip;       // optional, whole batch: instances flagged non-zero are not solved (SQP: already converged)
 };
+
+// Explicit max-norms of the dynamics and bound-slack residuals of a group's QP iterate (see explicit_residuals in
+// mpcb_qp.cuh), for the groups with `act` set; warp-uniform control flow.
+template <int NX, int NU>
+MPCB_DEV void qp8_explicit_residuals(const double *__restrict__ ws, int N, bool act, double &res_b, double &res_d)
+{
+    using L = Layout<NX, NU>;
+    constexpr int NZ = L::NZ, NT = (NZ + kLPI - 1) / kLPI, NXT = (NX + kLPI - 1) / kLPI;
+    const int s = lane_id() & (kLPI - 1);
+    double eb = 0.0, ed = 0.0;
+    MPCB_NOUNROLL
+    for (int k = 0; k <= N; k++) {
+        const double *wk = ws + (size_t)k * L::STAGE;
+        MPCB_UNROLL
+        for (int t = 0; t < NT; t++) {
+            const int row = s + kLPI * t;
+            if (act && row < NZ && var_kind<NX, NU>(k, row, N).hasb) {
+                const double z = wk[L::O_Z + row];
+                ed = fmax(ed, fmax(fabs(z - wk[L::O_LB + row] - wk[L::O_TL + row]), fabs(wk[L::O_UB + row] - z - wk[L::O_TU + row])));
+            }
+        }
+        if (k < N) {
+            MPCB_UNROLL
+            for (int t = 0; t < NXT; t++) {
+                const int i = s + kLPI * t;
+                if (act && i < NX) {
+                    double a0 = wk[L::O_B + i] - wk[L::STAGE + L::O_Z + NU + i], a1 = 0.0;
+                    MPCB_UNROLL4
+                    for (int j = 0; j + 1 < NZ; j += 2) {
+                        a0 += wk[L::O_BAT + j * L::LDB + i] * wk[L::O_Z + j];
+                        a1 += wk[L::O_BAT + (j + 1) * L::LDB + i] * wk[L::O_Z + j + 1];
+                    }
+                    if (NZ & 1) a0 += wk[L::O_BAT + (NZ - 1) * L::LDB + i] * wk[L::O_Z + NZ - 1];
+                    eb = fmax(eb, fabs(a0 + a1));
+                }
+            }
+        }
+    }
+    res_b = grp_max(eb);
+    res_d = grp_max(ed);
+}
 
 // QP data and cold start of one instance (see F0 in mpcb_qp.cuh), for the groups with `act` set;
 // warp-uniform control flow, so the group reductions at the end are executed by every lane.
@@ -443,11 +485,21 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
     for (;;) {
         // ---- the stopping tests of mpcb_qp.cuh, in the same order (an instance that uses up its iterations is not tested again)
         auto test = [&]() {
+            bool cand = false;
             if (has && !done) {
                 if (git >= P.ipm_max_iter) { status = ST_MAXITER; done = true; }
                 else if (!(est_g == est_g) || !(est_b == est_b) || !(mu == mu)) { status = ST_NAN; done = true; }
                 else if (mu > kMuDiverge * mu0) { status = ST_MINSTEP; done = true; }
-                else if (est_g <= P.tol_stat && est_b <= P.tol_eq && est_d <= P.tol_ineq && comp <= P.tol_comp) { status = ST_OK; done = true; }
+                else if (est_g <= P.tol_stat && est_b <= P.tol_eq && est_d <= P.tol_ineq && comp <= P.tol_comp) cand = true;
+            }
+            // est_b / est_d are extrapolations (res_0 * prod(1 - alpha)): confirm them on the iterate itself before ST_OK
+            if (warp_or(cand ? 1 : 0)) {
+                double xb, xd;
+                qp8_explicit_residuals<NX, NU>(ws, N, cand, xb, xd);
+                if (cand) {
+                    if (xb <= P.tol_eq && xd <= P.tol_ineq) { status = ST_OK; done = true; }
+                    else { est_b = xb; est_d = xd; }
+                }
             }
         };
         test();
@@ -476,7 +528,11 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
         const bool want = !has && !drained;
         if (warp_or(want ? 1 : 0)) {
             int idx = 0;
-            if (want && s == 0) idx = (int)queue_take(job.next);
+            if (want && s == 0) {
+                idx = (int)queue_take(job.next);
+                if (job.skip)
+                    while (idx < job.B && job.skip[job.inst0 + idx]) idx = (int)queue_take(job.next);
+            }
             idx = warp_shfl(idx, lane & ~(kLPI - 1));
             const bool fresh = want && idx < job.B;
             if (want && !fresh) drained = true;

@@ -21,9 +21,15 @@ def shard_range(B: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def shard(t: torch.Tensor | None, B: int, rank: int, world: int):
-    """Slice the batch dimension of a per-instance tensor; shared tensors pass through."""
-    if t is None or t.dim() == 0 or t.shape[0] != B:
+    """Slice the batch dimension of a per-instance tensor; shared tensors pass through.
+
+    The solver's argument shapes decide which is which (``BlasterMPC._mode``): a 1-D tensor (yref[ny], p[25]) is
+    shared by every instance whatever its length -- B == ny must not slice it -- and a tensor of two or more
+    dimensions is per instance (x0[B,nx], yref[B,ny] / [B,N+1,ny], p[B,25] / [B,N,25]) and must lead with B."""
+    if t is None or t.dim() <= 1:
         return t
+    if t.shape[0] != B:
+        raise ValueError(f"per-instance tensor of shape {tuple(t.shape)} does not lead with the global batch size {B}")
     lo, hi = shard_range(B, rank, world)
     return t[lo:hi]
 

@@ -108,9 +108,14 @@ class BlasterMPC:
     """
 
     def __init__(self, mass, J, l_x, l_y, N, Tf, c, Q, R, Q_t, blastThruster, statesBound, controlBound, *,
-                 batch: int = 1, variant: int = 17, dtype=torch.float64, device=None, ws_batch: int = 0, ipm_max_iter: int = 60,
+                 batch: int = 1, variant: int = 17, dtype=torch.float64, device=None, ws_batch: int = 0, ipm_max_iter: int | None = None,
                  ipm_mu0: float = 1e2, ipm_thr0: float = -0.5, tol_stat: float = 1e-6, tol_eq: float = 1e-8,
-                 tol_ineq: float = 1e-8, tol_comp: float = 1e-8, alpha_min: float = 1e-8):
+                 tol_ineq: float = 1e-8, tol_comp: float = 1e-8, alpha_min: float = 1e-8, strict_reference: bool = False,
+                 throughput_batch: int = 0, qp8_batch: int = 0, qp8_warps: int = 0):
+        """``strict_reference`` restores the reference stack's solver semantics (mpcb_config.strict_reference,
+        include/mpcb.h): explicit residual norms in the stopping test, no early exit on diverging multipliers, the last
+        iterate applied on max-iter, and ``ipm_max_iter`` = 500 (blastermodel.py:279) unless given.  The default is
+        the throughput-oriented rule set with a cap of 60 iterations."""
         if dtype != torch.float64:
             raise NotImplementedError("only float64 is implemented: the reference computes in IEEE double and an interior "
                                       "point with active state bounds is not viable in FP32 (DESIGN.md)")
@@ -118,6 +123,12 @@ class BlasterMPC:
             raise MpcbError("BlasterMPC needs a CUDA device; this package has no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise MpcbError("BlasterMPC needs a CUDA device; this package has no CPU fallback")
+        if self.device.index is None:  # device='cuda' means the current CUDA device
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if ipm_max_iter is None:
+            ipm_max_iter = 500 if strict_reference else 60
         if variant not in (17, 12, 13):
             raise ValueError("variant must be 17 (BLASTER17), 12 (QUAD12) or 13 (QUAT13)")
         self.nx, self.nu = {17: (17, 6), 12: (12, 4), 13: (13, 4)}[int(variant)]
@@ -138,6 +149,8 @@ class BlasterMPC:
         cfg.ipm_max_iter, cfg.ipm_mu0, cfg.ipm_thr0 = ipm_max_iter, ipm_mu0, ipm_thr0
         cfg.tol_stat, cfg.tol_eq, cfg.tol_ineq, cfg.tol_comp, cfg.alpha_min = tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min
         cfg.dtype, cfg.max_batch, cfg.ws_batch, cfg.device = 64, self.batch, ws_batch, self.device.index
+        cfg.strict_reference, cfg.throughput_batch, cfg.qp8_batch, cfg.qp8_warps = int(bool(strict_reference)), int(throughput_batch), int(qp8_batch), int(qp8_warps)
+        self.strict_reference = bool(strict_reference)
         self.cfg = cfg
         self._h = C.c_void_p()
         if self.lib.mpcb_create(C.byref(cfg), C.byref(self._h)) != 0:
@@ -189,11 +202,12 @@ class BlasterMPC:
         return t
 
     def _mode(self, t, B, per_stage_rows, width, name):
-        if t.dim() == 1:
+        """SHARED / PER_INSTANCE / PER_STAGE from the exact shape of a torch tensor or NumPy array."""
+        if t.ndim == 1 and tuple(t.shape) == (width,):
             return MPCB_SHARED
-        if t.dim() == 2 and t.shape == (B, width):
+        if t.ndim == 2 and tuple(t.shape) == (B, width):
             return MPCB_PER_INSTANCE
-        if t.dim() == 3 and t.shape == (B, per_stage_rows, width):
+        if t.ndim == 3 and tuple(t.shape) == (B, per_stage_rows, width):
             return MPCB_PER_STAGE
         raise ValueError(f"{name}: shape {tuple(t.shape)} is none of [{width}], [B,{width}], [B,{per_stage_rows},{width}]")
 
@@ -222,11 +236,17 @@ class BlasterMPC:
         with torch.cuda.device(self.device):
             self._check(self.lib.mpcb_shift(self._h, B, self._stream()), "mpcb_shift")
 
-    def solve(self, x0, yref, p=None, want_traj: bool = True, sqp_iters: int = 1):
+    def solve(self, x0, yref, p=None, want_traj: bool = True, sqp_iters: int = 1, sqp_tol=None):
         """One SQP-RTI iteration for every instance: returns (u0[B,nu], X[B,N+1,nx],
         U[B,N,nu], status[B] int32).  yref: [ny] | [B,ny] | [B,N+1,ny]; p: None | [25] |
         [B,25] | [B,N,25].  The iterate is kept in the handle for the next call (un-shifted
-        warm start, as the reference's loop does)."""
+        warm start, as the reference's loop does).
+
+        ``sqp_iters`` > 1 or ``sqp_tol`` given: multi-iteration SQP (mpcb_solve_sqp).  ``sqp_tol`` = a float or
+        (stat, eq, ineq, comp): iterate to convergence, at most ``sqp_iters`` QPs per instance (the reference's
+        options: nlp_solver_tol_* = 1e-6, nlp_solver_max_iter = 100); then ``status`` is the SQP status, ``self.iters``
+        the summed interior-point iterations, ``self.sqp_iters`` the QPs solved and ``self.nlp_res[B,4]`` the residuals
+        of the final iterate."""
         with torch.cuda.device(self.device):
             x0 = self._t(x0, (self.nx,), "x0")
             B = x0.shape[0] if x0.dim() == 2 else 1
@@ -242,13 +262,20 @@ class BlasterMPC:
             U = torch.empty((B, self.N, self.nu), dtype=torch.float64, device=self.device) if want_traj else None
             status = torch.empty((B,), dtype=torch.int32, device=self.device)
             self.iters = torch.empty((B,), dtype=torch.int32, device=self.device)
-            if sqp_iters == 1:
+            if sqp_iters == 1 and sqp_tol is None:
                 rc = self.lib.mpcb_solve(self._h, self._p(x0), self._p(yref), ymode, self._p(pt), pmode, self._p(u0),
                                          self._p(X), self._p(U), self._p(status), self._p(self.iters), B, self._stream())
-            else:  # full SQP: re-linearise sqp_iters times on the same data
+            else:  # SQP: re-linearise on the same data, to convergence when tolerances are given
+                tol = None
+                if sqp_tol is not None:
+                    t = np.broadcast_to(np.asarray(sqp_tol, dtype=np.float64), (4,)).copy()
+                    tol = (C.c_double * 4)(*t)
+                self.sqp_iters = torch.empty((B,), dtype=torch.int32, device=self.device)
+                self.nlp_res = torch.empty((B, 4), dtype=torch.float64, device=self.device)
                 rc = self.lib.mpcb_solve_sqp(self._h, self._p(x0), self._p(yref), ymode, self._p(pt), pmode, int(sqp_iters),
-                                             self._p(u0), self._p(X), self._p(U), self._p(status), self._p(self.iters), B,
-                                             self._stream())
+                                             None if tol is None else C.cast(tol, C.c_void_p), self._p(u0), self._p(X), self._p(U),
+                                             self._p(status), self._p(self.iters), self._p(self.sqp_iters), self._p(self.nlp_res),
+                                             B, self._stream())
             self._check(rc, "mpcb_solve")
             self._yref = yref
         return u0, X, U, status
@@ -262,6 +289,7 @@ class BlasterMPC:
         (defaults = simulation_blaster.py:12-21)."""
         a = acados_json_args(path, N=N)
         J = np.diag([0.50781, 0.47314, 0.72975]) if J is None else J
+        kw.setdefault("ipm_max_iter", a["ipm_max_iter"])  # qp_solver_iter_max of the dump (500 in the reference's) unless overridden
         return cls(mass, J, l_x, l_y, a["N"], a["Tf"], c, a["Q"], a["R"], a["Q_t"], a["blastThruster"], a["statesBound"],
                    a["controlBound"], batch=batch, variant=variant, **kw)
 
@@ -278,14 +306,18 @@ class BlasterMPC:
 
     def solve_host(self, x0, yref, p=None, want_traj: bool = False):
         """Same through ``mpcb_solve_host``: NumPy in, NumPy out, copies inside the call."""
-        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, self.nx)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        if x0.shape[-1] != self.nx or x0.ndim > 2:
+            raise ValueError(f"x0: expected [B,{self.nx}] or [{self.nx}], got {x0.shape}")
+        x0 = x0.reshape(-1, self.nx)
         B = x0.shape[0]
+        # the library copies B*ny / B*(N+1)*ny / B*N*25 doubles straight from these pointers: validate the shapes first
         yref = np.ascontiguousarray(yref, dtype=np.float64)
-        ymode = {1: MPCB_SHARED, 2: MPCB_PER_INSTANCE, 3: MPCB_PER_STAGE}[yref.ndim]
+        ymode = self._mode(yref, B, self.N + 1, self.ny, "yref")
         pmode, pp = MPCB_SHARED, None
         if p is not None:
             p = np.ascontiguousarray(p, dtype=np.float64)
-            pmode, pp = {1: MPCB_SHARED, 2: MPCB_PER_INSTANCE, 3: MPCB_PER_STAGE}[p.ndim], p.ctypes.data
+            pmode, pp = self._mode(p, B, self.N, 25, "p"), p.ctypes.data
         u0 = np.empty((B, self.nu))
         X = np.empty((B, self.N + 1, self.nx)) if want_traj else None
         U = np.empty((B, self.N, self.nu)) if want_traj else None
@@ -386,6 +418,19 @@ class BlasterMPC:
             self._check(self.lib.mpcb_command_map(self._h, self._p(x), self._p(u0), self._p(quat), self._p(thrust), B,
                                                   self._stream()), "mpcb_command_map")
         return quat, thrust
+
+    def debug_qp(self, B: int | None = None):
+        """Test hook (mpcb_debug_qp): the interior-point iterate the last ``solve`` ended with and the QP it solved, as a
+        dict of tensors -- z, tl, tu, ll, lu, lb, ub, g [B,N+1,nz]; pi [B,N+1,nx]; BAt [B,N,nz,nx]; b [B,N,nx]."""
+        B = self.batch if B is None else B
+        nz, N, nx = self.nx + self.nu, self.N, self.nx
+        with torch.cuda.device(self.device):
+            mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=self.device)
+            o = {k: mk(B, N + 1, nz) for k in ("z", "tl", "tu", "ll", "lu", "lb", "ub", "g")}
+            o["pi"], o["BAt"], o["b"] = mk(B, N + 1, nx), mk(B, N, nz, nx), mk(B, N, nx)
+            self._check(self.lib.mpcb_debug_qp(self._h, *[self._p(o[k]) for k in ("z", "pi", "tl", "tu", "ll", "lu", "lb", "ub", "g", "BAt", "b")],
+                                               B, self._stream()), "mpcb_debug_qp")
+        return o
 
     def profile(self, enable: bool = True):
         self._check(self.lib.mpcb_profile(self._h, int(enable)), "mpcb_profile")

@@ -491,7 +491,7 @@ class IPMResult:
 
 
 def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8, mu0=1e2, thr0=-0.5,
-              max_iter=60, alpha_min=1e-8, z_fixed=None) -> IPMResult:
+              max_iter=None, alpha_min=1e-8, z_fixed=None, strict=False) -> IPMResult:
     """Mehrotra predictor-corrector IPM, cold start [upstream D8], default tolerances =
     HPIPM's documented defaults (stationarity 1e-6, the rest 1e-8).  Same iteration
     (initial point, centering rule, single step length for primal and dual, step
@@ -501,8 +501,15 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
 
     The linear residuals (stationarity, dynamics, bound-slack) enter the stopping test
     through their exact-arithmetic values |r_0| * prod(1 - alpha_j): they are affine in
-    the iterate and everything takes the same step (DESIGN.md "stopping test").  ``res``
-    also carries the explicitly evaluated norms for the tests."""
+    the iterate and everything takes the same step (DESIGN.md "stopping test"); before success
+    is reported the two that can be evaluated exactly (equality, bound slacks) are confirmed on
+    the iterate itself.  ``res`` also carries the explicitly evaluated norms for the tests.
+
+    ``strict`` (mpcb_config.strict_reference): the reference stack's semantics -- the explicit norms
+    (stationarity included) decide the stopping test, there is no early exit on diverging multipliers,
+    and the iteration cap defaults to 500 (blastermodel.py:279) instead of 60."""
+    if max_iter is None:
+        max_iter = 500 if strict else 60
     n, m = g.size, c.size
     il, iu = np.isfinite(lb), np.isfinite(ub)
     lbf = np.where(il, lb, 0.0)
@@ -534,16 +541,18 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
                     max(np.abs(r_dl).max(initial=0.0), np.abs(r_du).max(initial=0.0)))
         if rg_est is None:
             rg_est, rb_est, rd_est = explicit
-        res = (rg_est, rb_est, rd_est, comp) + explicit
+        res = ((explicit if strict else (rg_est, rb_est, rd_est)) + (comp,)) + explicit
         if not np.isfinite(res[0] + res[1] + mu):
             status = 1
             break
-        if mu > 1e2 * mu0:  # diverging multipliers = infeasible QP: stop early, same status as the min-step exit
+        if not strict and mu > 1e2 * mu0:  # diverging multipliers = infeasible QP: stop early, same status as the min-step exit
             status = 3
             break
         if res[0] <= tol_stat and res[1] <= tol_eq and res[2] <= tol_ineq and comp <= tol_comp:
-            status = 0
-            break
+            if strict or (explicit[1] <= tol_eq and explicit[2] <= tol_ineq):
+                status = 0
+                break
+            rb_est, rd_est = explicit[1], explicit[2]  # the extrapolation was too optimistic: go on from the measured values
         gam = ll / tl + lu / tu
         K[np.arange(n), np.arange(n)] = H + gam
         lu_piv = _lu_factor(K)
@@ -677,6 +686,7 @@ class RTIOracle:
     def __init__(self, P: BlasterProblem, **ipm_opts):
         self.P = P
         self.ipm_opts = ipm_opts
+        self.strict = bool(ipm_opts.get("strict", False))
         self.reset()
 
     def reset(self, x_init=None, u_init=None):
@@ -695,7 +705,9 @@ class RTIOracle:
         du, dx, r = solve_qp(qp, **self.ipm_opts)
         # FIXED_STEP, step length 1.0 (JSON globalization / nlp_solver_step_length):
         # full step, no SQP-level line search; [upstream D5] iterate kept, not shifted
-        if r.status == 0:  # a failed QP leaves the iterate untouched (same rule as the product)
+        # a failed QP leaves the iterate untouched (same rule as the product); with the reference's semantics the last
+        # interior-point iterate is applied when the iteration cap was hit, as acados does
+        if r.status == 0 or (self.strict and r.status == 2):
             self.X = self.X + dx
             self.U = self.U + du
         self.last = (qp, r)
@@ -704,6 +716,52 @@ class RTIOracle:
 
     def cost(self):
         return stage_cost(self.X, self.U, self._yref, self.P)
+
+    # ---- SQP to convergence (acados' SQP loop with nlp_solver_max_iter / nlp_solver_tol_*)
+    def nlp_residuals(self, x0, yref, p=None, pi=None, lam_l=None, lam_u=None):
+        """inf-norms (stat, eq, ineq, comp) at the stored iterate for the multipliers of the last QP (dense ordering of
+        ``qp_to_dense``: pi over the N dynamics rows, lam over z = [du_0, dx_1, du_1, ..., dx_N])."""
+        P = self.P
+        qp = build_qp(self.X, self.U, np.asarray(x0, dtype=np.float64), yref, p, P)
+        H, g, C, c, lb, ub = qp_to_dense(qp)
+        n = g.size
+        pi = np.zeros(c.size) if pi is None else pi
+        lam_l = np.zeros(n) if lam_l is None else lam_l
+        lam_u = np.zeros(n) if lam_u is None else lam_u
+        il, iu = np.isfinite(lb), np.isfinite(ub)
+        # at dz = 0 the QP gradient g is the NLP cost gradient and C'pi the dynamics term of the Lagrangian
+        stat = np.abs(g + C.T @ pi - lam_l + lam_u).max()
+        eq = max(np.abs(qp.b).max(), np.abs(qp.dx0).max())
+        # lb / ub are bounds on the increment: lb = bound - value, so the violation of the iterate is max(lb, -ub, 0)
+        ineq = max(np.max(np.where(il, lb, -np.inf), initial=0.0), np.max(np.where(iu, -ub, -np.inf), initial=0.0))
+        comp = max(np.max(np.abs(np.where(il, lam_l * lb, 0.0)), initial=0.0), np.max(np.abs(np.where(iu, lam_u * ub, 0.0)), initial=0.0))
+        return stat, eq, ineq, comp
+
+    def sqp_solve(self, x0, yref, p=None, max_iter=100, tol=1e-6):
+        """-> (u0, X, U, status, sqp_iters, qp_iters, res): status 0 converged, 2 max_iter, 4 QP failure, 1 NaN."""
+        tol = np.broadcast_to(np.asarray(tol, dtype=np.float64), (4,))
+        pi = lam_l = lam_u = None
+        n_qp = qp_it = 0
+        status = 2
+        for it in range(max_iter + 1):
+            res = self.nlp_residuals(x0, yref, p, pi, lam_l, lam_u)
+            if not np.isfinite(res[0] + res[1]):
+                status = 1
+                break
+            if all(r <= t for r, t in zip(res, tol)):
+                status = 0
+                break
+            if it == max_iter:
+                break
+            _, _, _, st = self.solve(x0, yref, p)
+            r = self.last[1]
+            n_qp += 1
+            qp_it += r.iters
+            if not (st == 0 or (self.strict and st == 2)):
+                status = 1 if st == 1 else 4
+                break
+            pi, lam_l, lam_u = r.pi, r.lam_l, r.lam_u
+        return self.U[0].copy(), self.X.copy(), self.U.copy(), status, n_qp, qp_it, res
 
 
 def closed_loop(P: BlasterProblem, x0, yref, p=None, steps=10, **ipm_opts):

@@ -16,7 +16,8 @@ class OrcProblem(C.Structure):
                 ("c", C.c_double), ("Q", C.c_double * 17), ("R", C.c_double * 6), ("Qt", C.c_double * 17),
                 ("lbx", C.c_double * 17), ("ubx", C.c_double * 17), ("lbu", C.c_double * 6), ("ubu", C.c_double * 6),
                 ("ipm_max_iter", C.c_int), ("rg_mode", C.c_int), ("ric_alg", C.c_int), ("ipm_mu0", C.c_double), ("ipm_thr0", C.c_double),
-                ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double), ("alpha_min", C.c_double)]
+                ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double), ("alpha_min", C.c_double),
+                ("strict", C.c_int), ("reserved_", C.c_int)]
 
 
 _lib = None
@@ -29,6 +30,7 @@ def lib():
         _lib = C.CDLL(path)
         assert _lib.orc_problem_size() == C.sizeof(OrcProblem)
         _lib.orc_rti_solve_batch.restype = C.c_int
+        _lib.orc_sqp_solve_batch.restype = C.c_int
         _lib.orc_max_threads.restype = C.c_int
     return _lib
 
@@ -37,9 +39,14 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def make_problem(P: BlasterProblem, max_iter=60, mu0=1e2, thr0=-0.5, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8,
-                 tol_comp=1e-8, ric_alg=1, rg_mode=2, alpha_min=1e-8) -> OrcProblem:
+def make_problem(P: BlasterProblem, max_iter=None, mu0=1e2, thr0=-0.5, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8,
+                 tol_comp=1e-8, ric_alg=1, rg_mode=2, alpha_min=1e-8, strict=False) -> OrcProblem:
+    """``strict``: the reference stack's semantics (mpcb_config.strict_reference) -- explicit residual norms in the stopping
+    test, no divergence exit, last iterate applied on max-iter, iteration cap 500 (blastermodel.py:279) unless given."""
     o = OrcProblem()
+    if max_iter is None:
+        max_iter = 500 if strict else 60
+    o.strict = int(bool(strict))
     o.variant, o.N, o.dt, o.mass = P.variant, P.N, P.dt, P.mass
     o.J[:] = P.J.reshape(-1)
     o.Jinv[:] = P.Jinv.reshape(-1)
@@ -125,3 +132,23 @@ class BatchRTI:
                                        self.iters.ctypes.data_as(C.POINTER(C.c_int32)), B, self.nthreads)
         assert rc == 0
         return self.U[:, 0].copy(), self.X.copy(), self.U.copy(), self.status.copy()
+
+    def sqp_solve(self, x0, yref, p=None, max_iter=100, tol=1e-6):
+        """SQP to convergence: -> (u0, X, U, status, sqp_iters, qp_iters, res[B,4]).
+        tol: a float or (stat, eq, ineq, comp)."""
+        P, B = self.P, self.B
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(B, P.nx)
+        yref = np.ascontiguousarray(yref, dtype=np.float64)
+        ymode = {1: 0, 2: 1, 3: 2}[yref.ndim]
+        p = default_params() if p is None else np.ascontiguousarray(p, dtype=np.float64)
+        pmode = {1: 0, 2: 1, 3: 2}[p.ndim]
+        tol = np.ascontiguousarray(np.broadcast_to(np.asarray(tol, dtype=np.float64), (4,)))
+        sqp_it = np.zeros(B, dtype=np.int32)
+        qp_it = np.zeros(B, dtype=np.int32)
+        res = np.zeros((B, 4))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = lib().orc_sqp_solve_batch(C.byref(self.o), _dp(self.X), _dp(self.U), _dp(x0), _dp(yref), ymode, _dp(p), pmode, int(max_iter),
+                                       _dp(tol), ip(self.status), ip(sqp_it), ip(qp_it), _dp(res), B, self.nthreads)
+        assert rc == 0
+        self.iters = qp_it
+        return self.U[:, 0].copy(), self.X.copy(), self.U.copy(), self.status.copy(), sqp_it, qp_it, res

@@ -32,9 +32,13 @@ typedef struct {
     double dt, mass, J[9], Jinv[9], l_x, l_y, c;
     double Q[17], R[6], Qt[17], lbx[17], ubx[17], lbu[6], ubu[6];
     int ipm_max_iter;
-    int rg_mode; /* 0 stationarity residual tracked analytically, 1 recomputed from pi */
+    int rg_mode; /* 0 stationarity residual tracked analytically, 1 recomputed from pi and used in the test, 2 recomputed for the
+                    Newton right-hand side while the test uses the extrapolated norms, confirmed explicitly before success (the product's rule) */
     int ric_alg; /* 0 Cholesky of Hd+WW', 1 Householder LQ of [sqrt(Hd) | W] */
     double ipm_mu0, ipm_thr0, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min;
+    int strict; /* reference semantics (mpcb_config.strict_reference): explicit residual norms in the stopping test (rg_mode 1
+                   is then implied), no early exit on diverging multipliers, last iterate applied on max-iter */
+    int reserved_;
 } orc_problem;
 
 #define GRAV 9.81 /* blastermodel.py:93 */
@@ -330,6 +334,43 @@ int orc_rti_solve_batch(const orc_problem *P, double *X, double *U, const double
                                    pp, p_mode == 2, ws, &it);
             status[i] = st;
             iters[i] = it;
+        }
+        free(ws);
+    }
+    return fail ? -1 : 0;
+}
+
+/* SQP to convergence for B independent instances (see sqp_solve in mpc_oracle_body.h).  tol[4] = {stat, eq, ineq, comp};
+ * status[B], sqp_iters[B], qp_iters[B], res[B,4]. */
+int orc_sqp_solve_batch(const orc_problem *P, double *X, double *U, const double *x0, const double *yref, int yref_mode,
+                        const double *p, int p_mode, int max_iter, const double *tol, int32_t *status, int32_t *sqp_iters,
+                        int32_t *qp_iters, double *res, int B, int nthreads)
+{
+    const int nx = ORC_NX(P), nu = ORC_NU(P), ny = nx + nu, N = P->N;
+    const size_t wsz = P->variant == 17 ? b17_ws_doubles(N) : P->variant == 13 ? q13_ws_doubles(N) : q12_ws_doubles(N);
+    int fail = 0;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+        double *ws = (double *)malloc(wsz * sizeof(double));
+        if (!ws) {
+#pragma omp atomic write
+            fail = 1;
+        }
+#pragma omp for schedule(dynamic, 1)
+        for (int i = 0; i < B; i++) {
+            if (!ws) continue;
+            const double *yr = yref + (yref_mode == 0 ? 0 : yref_mode == 1 ? (size_t)i * ny : (size_t)i * (N + 1) * ny);
+            const double *pp = p + (p_mode == 0 ? 0 : p_mode == 1 ? (size_t)i * 25 : (size_t)i * N * 25);
+            int si = 0, qi = 0, st;
+            double *Xi = X + (size_t)i * (N + 1) * nx, *Ui = U + (size_t)i * N * nu;
+            if (P->variant == 17)
+                st = b17_sqp_solve(P, Xi, Ui, x0 + (size_t)i * nx, yr, yref_mode == 2, pp, p_mode == 2, max_iter, tol, ws, &si, &qi, res + (size_t)i * 4);
+            else if (P->variant == 13)
+                st = q13_sqp_solve(P, Xi, Ui, x0 + (size_t)i * nx, yr, yref_mode == 2, pp, p_mode == 2, max_iter, tol, ws, &si, &qi, res + (size_t)i * 4);
+            else
+                st = q12_sqp_solve(P, Xi, Ui, x0 + (size_t)i * nx, yr, yref_mode == 2, pp, p_mode == 2, max_iter, tol, ws, &si, &qi, res + (size_t)i * 4);
+            status[i] = st; sqp_iters[i] = si; qp_iters[i] = qi;
         }
         free(ws);
     }

@@ -348,7 +348,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
             for (int j = 0; j < NZ; j++) {
                 size_t i = (size_t)k * NZ + j;
                 if (SKIP(k, j)) { w->rg[i] = 0; continue; }
-                if (it == 0 || P->rg_mode >= 1) {
+                if (it == 0 || P->rg_mode >= 1 || P->strict) {
                     double r = w->H0[i] * w->z[i] + w->g[i] - w->ll[i] + w->lu[i];
                     if (k < N) for (int c = 0; c < NX; c++) r += BAt[j * NX + c] * w->pi[(size_t)(k + 1) * NX + c];
                     if (j >= NU) r -= w->pi[(size_t)k * NX + j - NU];
@@ -379,13 +379,20 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
         if (nb) mu /= nb;
         if (it == 0) { rg_est = res_g; rb_est = res_b; rd_est = res_d; }
         /* the three linear residuals are affine in the iterate and everything takes the same
-         * step, so each shrinks by exactly (1-alpha); the stopping test uses those values */
-        if (P->rg_mode == 2) { res_g = rg_est; res_b = rb_est; res_d = rd_est; }
+         * step, so each shrinks by exactly (1-alpha); the stopping test uses those values, and
+         * confirms the two that can be evaluated exactly (dynamics, bound slacks) on the iterate
+         * itself before it reports success */
+        const int extrap = P->rg_mode == 2 && !P->strict;
+        const double xb = res_b, xd = res_d;
+        if (extrap) { res_g = rg_est; res_b = rb_est; res_d = rd_est; }
         if (orc_debug()) fprintf(stderr, "it %d res_g %.3e res_b %.3e res_d %.3e comp %.3e mu %.3e\n", it, res_g, res_b, res_d, comp, mu);
         if (!(res_g == res_g) || !(res_b == res_b) || !(mu == mu)) { status = 1; break; }
         /* diverging multipliers = infeasible QP: stop early, same status as the min-step exit */
-        if (mu > 1e2 * mu0) { status = 3; break; }
-        if (res_g <= P->tol_stat && res_b <= P->tol_eq && res_d <= P->tol_ineq && comp <= P->tol_comp) { status = 0; break; }
+        if (!P->strict && mu > 1e2 * mu0) { status = 3; break; }
+        if (res_g <= P->tol_stat && res_b <= P->tol_eq && res_d <= P->tol_ineq && comp <= P->tol_comp) {
+            if (!extrap || (xb <= P->tol_eq && xd <= P->tol_ineq)) { status = 0; break; }
+            rb_est = xb; rd_est = xd;
+        }
         /* factorise with barrier diagonal */
         for (size_t i = 0; i < n; i++) w->Hd[i] = w->H0[i] + w->ll[i] / w->tl[i] + w->lu[i] / w->tu[i];
         if (orc_debug()) {
@@ -429,7 +436,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
         /* the stationarity residual is affine in (z, pi, lam) and all take the same step, so
          * r_g <- (1-alpha) r_g exactly; evaluating it explicitly needs the multipliers of
          * numerically pinned states, whose absolute accuracy degrades like eps*lam/t. */
-        if (P->rg_mode == 0) for (size_t i = 0; i < n; i++) w->rg[i] *= (1.0 - alpha);
+        if (P->rg_mode == 0 && !P->strict) for (size_t i = 0; i < n; i++) w->rg[i] *= (1.0 - alpha);
         rg_est *= (1.0 - alpha); rb_est *= (1.0 - alpha); rd_est *= (1.0 - alpha);
         if (!(alpha >= P->alpha_min)) { status = (alpha == alpha) ? 3 : 1; it++; break; } /* [upstream D9] 3 = min step */
     }
@@ -478,12 +485,83 @@ static int SFX(rti_solve)(const orc_problem *P, double *X, double *U, const doub
     /* [upstream D3] x0 pinned: dx_0 = x0 - X_0 */
     for (int i = 0; i < NX; i++) w.z[NU + i] = x0[i] - X[i];
     int status = SFX(ipm)(P, &w, N, iters);
-    /* a failed QP leaves the iterate untouched (same rule as the product) */
-    for (int k = 0; k <= (status == 0 ? N : -1); k++) {
+    /* a failed QP leaves the iterate untouched (same rule as the product); with reference
+     * semantics the last iterate is applied when the iteration cap was hit, as acados does */
+    const int take = status == 0 || (P->strict && status == 2);
+    for (int k = 0; k <= (take ? N : -1); k++) {
         if (k < N) for (int j = 0; j < NU; j++) U[(size_t)k * NU + j] += w.z[(size_t)k * NZ + j];
         for (int i = 0; i < NX; i++) X[(size_t)k * NX + i] += w.z[(size_t)k * NZ + NU + i];
     }
     return status;
+}
+/* ---- multi-iteration SQP to convergence on one instance (acados' SQP loop with the options the
+ * reference's dump carries: nlp_solver_max_iter, nlp_solver_tol_stat/eq/ineq/comp).  Each iteration: linearise, evaluate
+ * the NLP residuals with the multipliers of the previous QP (zero at the start [upstream D4]), stop if all four are within
+ * tolerance, else solve the QP and take the full step.  One more evaluation after the max_iter-th QP reports the final
+ * iterate's residuals (and counts as convergence if they pass).  res[4] = {stat, eq, ineq, comp}.
+ * Returns 0 converged, 2 max_iter, 4 QP failure, 1 NaN; *sqp_iters = QPs solved, *qp_iters = IPM iterations in total. */
+static int SFX(sqp_solve)(const orc_problem *P, double *X, double *U, const double *x0, const double *yref, int yref_per_stage,
+                          const double *p, int p_per_stage, int max_iter, const double *tol, double *wsmem, int *sqp_iters,
+                          int *qp_iters, double *res)
+{
+    const int N = P->N, NY = NZ;
+    SFX(ws_t) w;
+    SFX(ws_bind)(&w, wsmem, N);
+    const size_t n = (size_t)(N + 1) * NZ;
+    for (size_t i = 0; i < n; i++) { w.ll[i] = 0.0; w.lu[i] = 0.0; }
+    for (size_t i = 0; i < (size_t)(N + 1) * NX; i++) w.pi[i] = 0.0;
+    *sqp_iters = 0; *qp_iters = 0;
+    for (int it = 0; it <= max_iter; it++) {
+        /* linearisation at the current iterate */
+        for (int k = 0; k < N; k++) {
+            const double *pk = p + (p_per_stage ? (size_t)k * 25 : 0);
+            double xn[NX];
+            SFX(rk4_sens)(P, X + (size_t)k * NX, U + (size_t)k * NU, pk, xn, w.BAt + (size_t)k * NZ * NX);
+            for (int i = 0; i < NX; i++) w.b[(size_t)k * NX + i] = xn[i] - X[(size_t)(k + 1) * NX + i];
+        }
+        double rs = 0, re = 0, ri = 0, rc = 0;
+        for (int k = 0; k <= N; k++) {
+            const double *yr = yref + (yref_per_stage ? (size_t)k * NY : 0);
+            const double *BAt = w.BAt + (size_t)k * NZ * NX;
+            for (int j = 0; j < NZ; j++) {
+                if (SKIP(k, j)) continue;
+                const size_t i = (size_t)k * NZ + j;
+                const int isu = j < NU;
+                const double y = isu ? U[(size_t)k * NU + j] : X[(size_t)k * NX + j - NU];
+                const double yv = isu ? yr[NX + j] : yr[j - NU];
+                const double wgt = isu ? P->dt * P->R[j] : (k < N ? P->dt * P->Q[j - NU] : P->Qt[j - NU]);
+                const int hasb = isu ? 1 : (k >= 1 && k < N);
+                double r = wgt * (y - yv);
+                if (k < N) for (int c = 0; c < NX; c++) r += BAt[j * NX + c] * w.pi[(size_t)(k + 1) * NX + c];
+                if (!isu) r -= w.pi[(size_t)k * NX + j - NU];
+                if (hasb) {
+                    const double lb = isu ? P->lbu[j] : P->lbx[j - NU], ub = isu ? P->ubu[j] : P->ubx[j - NU];
+                    r += w.lu[i] - w.ll[i];
+                    ri = fmax(ri, fmax(lb - y, y - ub));
+                    rc = fmax(rc, fmax(fabs(w.ll[i] * (y - lb)), fabs(w.lu[i] * (ub - y))));
+                }
+                rs = fmax(rs, fabs(r));
+            }
+            if (k < N) for (int c = 0; c < NX; c++) re = fmax(re, fabs(w.b[(size_t)k * NX + c]));
+            if (k == 0) for (int c = 0; c < NX; c++) re = fmax(re, fabs(x0[c] - X[c]));
+        }
+        if (res) { res[0] = rs; res[1] = re; res[2] = ri; res[3] = rc; }
+        if (!(rs == rs) || !(re == re)) return 1;
+        if (rs <= tol[0] && re <= tol[1] && ri <= tol[2] && rc <= tol[3]) return 0;
+        if (it == max_iter) break;
+        /* QP of this iterate (same assembly as rti_solve) */
+        int qit = 0;
+        const int st = SFX(rti_solve)(P, X, U, x0, yref, yref_per_stage, p, p_per_stage, wsmem, &qit);
+        *sqp_iters += 1; *qp_iters += qit;
+        if (!(st == 0 || (P->strict && st == 2))) return st == 1 ? 1 : 4;
+        /* multipliers of components without bounds are not part of the QP: zero them for the residual */
+        for (size_t i = 0; i < n; i++) {
+            int k = (int)(i / NZ), j = (int)(i % NZ);
+            const int hasb = !SKIP(k, j) && (j < NU || (k >= 1 && k < N));
+            if (!hasb) { w.ll[i] = 0.0; w.lu[i] = 0.0; }
+        }
+    }
+    return 2;
 }
 #undef SKIP
 #undef NZ

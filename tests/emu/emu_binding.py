@@ -24,7 +24,7 @@ class Params(C.Structure):
                 ("lbx", C.c_double * 17), ("ubx", C.c_double * 17), ("lbu", C.c_double * 6), ("ubu", C.c_double * 6),
                 ("ipm_max_iter", C.c_int), ("ipm_mu0", C.c_double), ("ipm_thr0", C.c_double),
                 ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double),
-                ("alpha_min", C.c_double)]
+                ("alpha_min", C.c_double), ("strict", C.c_int), ("reserved_", C.c_int)]
 
 
 def build(force=False):
@@ -50,10 +50,13 @@ def lib():
     return _lib
 
 
-def make_params(P, max_iter=60, mu0=1e2, thr0=-0.5, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
-                alpha_min=1e-8) -> Params:
+def make_params(P, max_iter=None, mu0=1e2, thr0=-0.5, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
+                alpha_min=1e-8, strict=False) -> Params:
     """P: oracle.blaster_oracle.BlasterProblem (only used here as a container of constants)."""
     o = Params()
+    if max_iter is None:
+        max_iter = 500 if strict else 60
+    o.strict = int(bool(strict))
     o.variant, o.N, o.dt, o.mass, o.inv_mass = P.variant, P.N, P.dt, P.mass, 1.0 / P.mass
     o.J[:] = P.J.reshape(-1)
     Jinv = np.linalg.inv(P.J)

@@ -16,7 +16,7 @@
 
 using namespace mpcb;
 
-template <int NX, int NU, int NSLOT>
+template <int NX, int NU, int NSLOT, bool STRICT = false>
 static int rti_one(const Params &P, double *X, double *U, const double *x0, const double *yref, int yps, const double *p,
                    int p_per_stage, int *iters, double *BAt_out, double *b_out)
 {
@@ -39,7 +39,7 @@ static int rti_one(const Params &P, double *X, double *U, const double *x0, cons
     memset(&sm, 0, sizeof(sm));
     emu::run_warp([&]() {
         int my_it = 0;
-        int st = qp_solve_warp<NX, NU, double, NSLOT>(P, sm, ws.data(), X, U, x0, yref, yps, &my_it);
+        int st = qp_solve_warp<NX, NU, double, NSLOT, STRICT>(P, sm, ws.data(), X, U, x0, yref, yps, &my_it);
         if (emu::lane() == 0) { status = st; it = my_it; }
     });
     *iters = it;
@@ -56,6 +56,11 @@ int emu_rti_solve(const Params *P, double *X, double *U, const double *x0, const
     // MPCB_EMU_NSLOT=1 exercises the single-buffer (throughput) variant
     const char *ns = getenv("MPCB_EMU_NSLOT");
     const bool one = ns && ns[0] == '1';
+    if (P->strict) {  // reference semantics: always the latency variant, as the host scheduler does
+        if (P->variant == 17) return rti_one<17, 6, 2, true>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+        if (P->variant == 13) return rti_one<13, 4, 2, true>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+        return rti_one<12, 4, 2, true>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
+    }
     if (P->variant == 17)
         return one ? rti_one<17, 6, 1>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out)
                    : rti_one<17, 6, 2>(*P, X, U, x0, yref, yps, p, p_per_stage, iters, BAt_out, b_out);
@@ -120,7 +125,7 @@ static void rti_four(const Params &P, int nb, double *X, double *U, const double
     unsigned next = 0;
     Qp8Batch job;
     job.X = X; job.U = U; job.x0 = x0; job.yref = yref; job.yref_stride = NX + NU; job.yps = 0;
-    job.ws = ws.data(); job.u0 = nullptr; job.status = status; job.iters = iters; job.inst0 = 0; job.B = nb; job.next = &next;
+    job.ws = ws.data(); job.u0 = nullptr; job.status = status; job.iters = iters; job.inst0 = 0; job.B = nb; job.next = &next; job.skip = nullptr;
     emu::run_warp([&]() { qp8_solve_queue<NX, NU>(P, sm, job); });
 }
 extern "C" void emu_rti_solve4(const Params *P, int nb, double *X, double *U, const double *x0, const double *yref, const double *p,
