@@ -15,6 +15,14 @@ own 1,024-instance batch (weak scaling), no collective on the solve path; one fi
 `e2e` goes through the C ABI's host entry point (mpcb_solve_host: pinned staging, H2D,
 solve, D2H) with NumPy buffers.  `cpu_baseline` / `--impl reference` time the C oracle
 (oracle/mpc_oracle.c, kind "port": acados/HPIPM cannot be built here) on the host cores.
+
+Beside the headline the line carries: `roofline` (the binding resource of the dominant kernel: the
+FP64 FMA pipe, achieved algorithmic TFLOP/s against the DFMA peak measured in the same run) and
+`roofline_hbm` (algorithmic bytes against MEASURED_PEAKS.json, with the ncu DRAM traffic);
+`solver.p50_ms / p99_ms` over >= 200 launches whatever --steps is; the explicit KKT residuals of
+the last solve's solutions; `zero_iterate` (acados' default all-zero initial iterate instead of
+(x0, hover trim)); `large_batch` (65,536 instances per GPU of BLASTER17 and QUAD12 on the
+four-instances-per-warp kernel, the kernel configs 3-5 run on, with its own roofline).
 """
 from __future__ import annotations
 
@@ -257,6 +265,101 @@ def run_gpu(args):
                   "mean_ipm_iters": float(q.iters.double().mean().item()), "converged_frac": float((qst == 0).double().mean().item())}
         del q
 
+    # ---- per-launch latency over >= 200 launches, whatever --steps is
+    lat_n = max(200, args.steps)
+    lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(lat_n)]
+    for a, b in lev:
+        mpc.reset(x0, trim)
+        flush.zero_()
+        a.record()
+        mpc.solve(x0, yref, want_traj=False)
+        b.record()
+    torch.cuda.synchronize()
+    lat_ms = np.array([a.elapsed_time(b) for a, b in lev])
+
+    # ---- explicit KKT residuals of the solutions of the last solve (evaluated from the exported QP data)
+    from mpc_blaster_b200 import diagnostics
+    kkt = {k: float(v[status == 0].max().item()) for k, v in diagnostics.explicit_kkt_residuals(mpc, B).items()}
+    max_iters_rank = torch.tensor([int(mpc.iters.max().item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(max_iters_rank) for _ in range(world)]
+        dist.all_gather(gathered, max_iters_rank)
+        max_iters_rank = torch.cat(gathered)
+    max_iters_rank = [int(v) for v in max_iters_rank.tolist()]
+
+    # ---- acados' default initial iterate (all zero) instead of (x0, hover trim)
+    zms = []
+    for i in range(3 + 10):
+        mpc.reset()
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _, _, _, zst = mpc.solve(x0, yref, want_traj=False)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            zms.append(a.elapsed_time(b))
+    zero_iterate = {"value": B / (float(np.mean(zms)) * 1e-3), "unit": UNIT + " per GPU", "ms_per_step": float(np.mean(zms)),
+                    "mean_ipm_iters": float(mpc.iters.double().mean().item()), "max_ipm_iters": int(mpc.iters.max().item()),
+                    "converged_frac": float((zst == 0).double().mean().item()),
+                    "note": "first solve from the all-zero iterate: the linearisation point violates x_0 = x0 by metres, so "
+                            "part of the batch has an infeasible linearised QP (status 3) and the rest needs more iterations"}
+    fp64_peak_early = mpc.fp64_peak_tflops()
+    del mpc
+
+    # ---- the large-batch kernel (qp8_kernel: four instances per warp), the one configs 3-5 run on
+    large = None
+    if not args.no_large:
+        large = {}
+        LB = args.large_batch
+        for variant in (17, 12):
+            lm = BlasterMPC.canonical(N=N, batch=LB, variant=variant)
+            lx_h, ly_h, lt_h = workload(rank, LB, variant)
+            lx, ly, lt = (torch.as_tensor(a, device=dev) for a in (lx_h, ly_h, lt_h))
+            lm.profile(True)
+            lms, lk2 = [], []
+            for i in range(2 + 5):
+                lm.reset(lx, lt)
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                lu0, _, _, lst = lm.solve(lx, ly, want_traj=False)
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    lms.append(a.elapsed_time(b))
+                    lk2.append(lm.last_kernel_ms()[1])
+            t = torch.tensor([sum(lms)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lit = float(lm.iters.double().mean().item())
+            lnx, lnu = lm.nx, lm.nu
+            lflops = algorithmic_flops_per_solve(lnx, lnu, N, lit) - algorithmic_flops_per_solve(lnx, lnu, N, 0)
+            k2s = float(np.mean(lk2)) * 1e-3
+            ent = {"value": LB * world * len(lms) / (float(t.item()) * 1e-3), "unit": UNIT, "batch_per_gpu": LB, "ms_per_step": float(t.item()) / len(lms),
+                   "kernel": f"qp8_kernel<{lnx},{lnu}>", "kernel_ms": k2s * 1e3, "mean_ipm_iters": lit,
+                   "converged_frac": float((lst == 0).double().mean().item()),
+                   "roofline": {"bound": "fp64_fma", "achieved": lflops * LB / k2s / 1e12, "peak": fp64_peak_early, "unit": "TFLOP/s",
+                                "frac": lflops * LB / k2s / 1e12 / fp64_peak_early},
+                   "roofline_hbm": {"achieved": algorithmic_bytes_per_solve(lnx, lnu, N) * LB / k2s / 1e9, "unit": "GB/s",
+                                    "algorithmic_bytes_per_launch": algorithmic_bytes_per_solve(lnx, lnu, N) * LB}}
+            if world == 1 and not args.no_cpu:
+                # spot check of this very launch against the C oracle (64 sampled instances)
+                from oracle import blaster_oracle as bo
+                from oracle import c_oracle as co
+                idx = np.sort(np.random.default_rng(7).choice(LB, 64, replace=False))
+                orc = co.BatchRTI(bo.canonical_problem(N, variant), len(idx), nthreads=len(os.sched_getaffinity(0)))
+                orc.reset(lx_h[idx], lt_h)
+                uo, _, _, sto = orc.solve(lx_h[idx], ly_h[idx])
+                ti = torch.as_tensor(idx, device=dev)
+                okk = sto == 0
+                ent["oracle_spot_check"] = {"instances": len(idx), "status_equal": bool((lst[ti].cpu().numpy() == sto).all()),
+                                            "iters_equal": bool((lm.iters[ti].cpu().numpy() == orc.iters).all()),
+                                            "max_du0": float(np.abs(lu0[ti].cpu().numpy()[okk] - uo[okk]).max())}
+            large[f"blaster{variant}" if variant == 17 else f"quad{variant}"] = ent
+            del lm
+            torch.cuda.empty_cache()
+
     # ---- final result gather (the only collective of the job)
     if world > 1:
         from mpc_blaster_b200.scheduler import gather_batch
@@ -282,14 +385,15 @@ def run_gpu(args):
     peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback B200_PROFILING.md"
     alg_bytes = algorithmic_bytes_per_solve(nx, nu, N) * B
     achieved_gbs = alg_bytes / k2 / 1e9
-    fp64_peak = mpc.fp64_peak_tflops()
+    fp64_peak = fp64_peak_early
     flops = algorithmic_flops_per_solve(nx, nu, N, iters_mean)
     f_lin_only = algorithmic_flops_per_solve(nx, nu, N, 0)
     qp_tflops = (flops - f_lin_only) * B / k2 / 1e12
     lin_tflops = f_lin_only * B / k1 / 1e12
-    traffic = None
+    traffic, ncu = None, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "qp_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "qp_kernel_traffic.json")))
+        traffic = ncu.get("dram_bytes_per_launch")
     except Exception:
         pass
 
@@ -309,15 +413,24 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x0_h.nbytes + yref_h.nbytes),
                     "d2h_bytes_per_step": int(B * nu * 8 + 2 * B * 4)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "qp_kernel<17,6>", "achieved": achieved_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k2 * 1e3,
-                         "note": "latency/FP64-pipe bound path: see fp64 for the binding resource"},
+            "roofline": {"bound": "fp64_fma", "kernel": "qp_kernel<17,6>", "achieved": qp_tflops, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": qp_tflops / fp64_peak, "traffic": traffic,
+                         "peak_source": "DFMA micro-kernel in this run (mpcb_fp64_peak); MEASURED_PEAKS.json carries no FP64 figure",
+                         "algorithmic_flops_per_launch": (flops - f_lin_only) * B, "kernel_ms": k2 * 1e3,
+                         "ncu_pipe_fp64_cycles_active_pct": ncu.get("sm__pipe_fp64_cycles_active_pct"),
+                         "ncu_issue_active_pct": ncu.get("smsp__issue_active_pct"),
+                         "note": "SURVEY 8(d): the path is bound by the FP64 CUDA-core pipe and the dependent chain of the stage "
+                                 "factorisation, not by HBM or the tensor cores (no FP64 tcgen05 kind)"},
+            "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes},
             "fp64": {"qp_kernel_tflops": qp_tflops, "linearize_kernel_tflops": lin_tflops, "peak_tflops_measured": fp64_peak,
                      "qp_frac": qp_tflops / fp64_peak, "linearize_kernel_ms": k1 * 1e3,
                      "algorithmic_mflop_per_solve": flops / 1e6},
-            "solver": {"mean_ipm_iters": iters_mean, "converged_frac": ok_frac,
-                       "p50_ms": float(np.percentile(step_ms, 50)), "p99_ms": float(np.percentile(step_ms, 99))},
+            "solver": {"mean_ipm_iters": iters_mean, "converged_frac": ok_frac, "max_ipm_iters_per_rank": max_iters_rank,
+                       "p50_ms": float(np.percentile(lat_ms, 50)), "p99_ms": float(np.percentile(lat_ms, 99)), "latency_launches": int(lat_n),
+                       "max_explicit_res_stat": kkt["stat"], "max_explicit_res_eq": kkt["eq"],
+                       "max_explicit_res_ineq": kkt["ineq"], "max_explicit_res_comp": kkt["comp"]},
+            "zero_iterate": zero_iterate, "large_batch": large,
             "cpu_baseline": cpu, "quad12": quad12}
     _emit(line)
     if world > 1:
@@ -348,6 +461,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-quad12", action="store_true")
+    ap.add_argument("--no-large", action="store_true", help="skip the 65,536-instance leg on the four-instances-per-warp kernel")
+    ap.add_argument("--large-batch", type=int, default=65536)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "graft" else args.warmup
     if args.impl == "reference":

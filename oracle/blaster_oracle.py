@@ -632,6 +632,37 @@ def kkt_certificate(H, g, C, c, lb, ub, z, pi, lam_l, lam_u):
     return dict(stat=stat, eq=eq, viol=viol, comp=comp, neg=neg)
 
 
+def explicit_kkt_residuals(P: "BlasterProblem", z, pi, tl, tu, ll, lu, lb, ub, g, BAt, b):
+    """Explicit KKT residuals of a batch of stage-ordered QP iterates, e.g. what the CUDA path's mpcb_debug_qp exports:
+    z, tl, tu, ll, lu, lb, ub, g [B,N+1,nz] with z_k = [du_k; dx_k]; pi [B,N+1,nx]; BAt [B,N,nz,nx] = [B_k'; A_k']; b [B,N,nx].
+    Everything is evaluated from the data, nothing is taken from the solver's own bookkeeping.  Returns per-instance
+    inf-norms: stat (Lagrangian gradient, Riccati sign convention H z + g - ll + lu + [B A]' pi_{k+1} - pi_k), eq
+    (dynamics), ineq (bound-slack identities), viol (true bound violation of z), comp (max lam * t), neg (most negative
+    slack or multiplier), and stat_comp [B,nz]: the stationarity norm per component of the stage variable."""
+    z, pi, tl, tu, ll, lu, lb, ub, g, BAt, b = (np.asarray(a, dtype=np.float64) for a in (z, pi, tl, tu, ll, lu, lb, ub, g, BAt, b))
+    N, nx, nu = P.N, P.nx, P.nu
+    nz = nx + nu
+    H = np.vstack([np.tile(np.concatenate([P.dt * P.R, P.dt * P.Q]), (N, 1)), np.concatenate([np.ones(nu), P.Qt])[None]])
+    k = np.arange(N + 1)[:, None]
+    j = np.arange(nz)[None, :]
+    var = np.where(j < nu, k < N, k >= 1)
+    hasb = np.where(j < nu, k < N, (k >= 1) & (k < N))
+    r = H * z + g - ll + lu
+    r[:, :N] += np.einsum("bkjc,bkc->bkj", BAt, pi[:, 1:])
+    r[:, :, nu:] -= pi
+    r = np.where(var, r, 0.0)
+    eq = b + np.einsum("bkjc,bkj->bkc", BAt, z[:, :N]) - z[:, 1:, nu:]
+    lbf, ubf = np.where(hasb, lb, 0.0), np.where(hasb, ub, 0.0)
+    rd = np.where(hasb, np.maximum(np.abs(z - lbf - tl), np.abs(ubf - z - tu)), 0.0)
+    viol = np.where(hasb, np.maximum(np.maximum(lbf - z, z - ubf), 0.0), 0.0)
+    comp = np.where(hasb, np.maximum(ll * tl, lu * tu), 0.0)
+    neg = np.where(hasb, np.maximum(np.maximum(-tl, -tu), np.maximum(-ll, -lu)), 0.0)
+    B = z.shape[0]
+    return dict(stat=np.abs(r).reshape(B, -1).max(1), eq=np.abs(eq).reshape(B, -1).max(1), ineq=rd.reshape(B, -1).max(1),
+                viol=viol.reshape(B, -1).max(1), comp=comp.reshape(B, -1).max(1), neg=neg.reshape(B, -1).max(1),
+                stat_comp=np.abs(r).max(1))
+
+
 def multipliers_from_primal(H, g, C, lb, ub, z, act_tol=1e-7):
     """Recover (pi, lam_l, lam_u) for a primal candidate z by least squares on the
     stationarity condition with multipliers only on (near-)active bounds.  Used to
@@ -734,7 +765,7 @@ class RTIOracle:
         eq = max(np.abs(qp.b).max(), np.abs(qp.dx0).max())
         # lb / ub are bounds on the increment: lb = bound - value, so the violation of the iterate is max(lb, -ub, 0)
         ineq = max(np.max(np.where(il, lb, -np.inf), initial=0.0), np.max(np.where(iu, -ub, -np.inf), initial=0.0))
-        comp = max(np.max(np.abs(np.where(il, lam_l * lb, 0.0)), initial=0.0), np.max(np.abs(np.where(iu, lam_u * ub, 0.0)), initial=0.0))
+        comp = max(np.max(np.abs(lam_l * np.where(il, lb, 0.0)), initial=0.0), np.max(np.abs(lam_u * np.where(iu, ub, 0.0)), initial=0.0))
         return stat, eq, ineq, comp
 
     def sqp_solve(self, x0, yref, p=None, max_iter=100, tol=1e-6):

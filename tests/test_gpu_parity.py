@@ -376,7 +376,7 @@ def test_api_misuse_is_reported_not_crashed(cuda_device):
         BlasterMPC.canonical(N=5, batch=2, statesBound=sb)
 
 
-def test_million_instance_chunking_smoke(cuda_device, monkeypatch):
+def test_million_instance_chunking_smoke(cuda_device):
     """Config 5 scale check (reduced): 213k instances through a workspace of 32k instances (six full chunks and one of 16,384) --
     chunk boundaries must not change results (compare the first and last chunk against a fresh solver).
     Chunks of this size run on the four-instances-per-warp kernel, whose persistent warps hand the
@@ -387,9 +387,8 @@ def test_million_instance_chunking_smoke(cuda_device, monkeypatch):
     big = _mpc(N, B, ws_batch=C)
     u0, _, _, st = big.solve(x0, yref, want_traj=False)
     assert float((st == 0).double().mean()) > 0.99
-    monkeypatch.setenv("MPCB_QP8_BATCH", "1")
     for lo in (0, B - 1000):
-        small = _mpc(N, 1000)
+        small = _mpc(N, 1000, qp8_batch=1)
         us, _, _, ss = small.solve(x0[lo:lo + 1000], yref[lo:lo + 1000], want_traj=False)
         assert torch.equal(us, u0[lo:lo + 1000]) and torch.equal(ss, st[lo:lo + 1000])
 
@@ -481,17 +480,15 @@ def test_poc_jacobian_generator(cuda_device):
 
 
 @pytest.mark.parametrize("variant,N,B", [(12, 20, 1024), (17, 20, 515), (12, 40, 130), (17, 7, 5)])
-def test_four_instances_per_warp_kernel_matches_c_oracle(cuda_device, variant, N, B, monkeypatch):
+def test_four_instances_per_warp_kernel_matches_c_oracle(cuda_device, variant, N, B):
     """The throughput variant of the QP kernel (mpcb_qp8.cuh: four instances per warp), forced for
     every chunk size, against the C oracle on identical inputs -- including batch sizes that leave
     the last warp partly empty -- and against the one-instance-per-warp kernel."""
     P = bo.canonical_problem(N, variant)
     x0, yref = sc.random_setpoints(B, seed=77, nx=P.nx, nu=P.nu)
     trim = sc.hover_trim(P.nu)
-    monkeypatch.setenv("MPCB_QP8_BATCH", "1")
-    mpc8 = _mpc(N, B, variant)
-    monkeypatch.setenv("MPCB_QP8_BATCH", str(1 << 30))
-    mpc1 = _mpc(N, B, variant)
+    mpc8 = _mpc(N, B, variant, qp8_batch=1)
+    mpc1 = _mpc(N, B, variant, qp8_batch=1 << 30)
     orc = co.BatchRTI(P, B)
     for m in (mpc8, mpc1, orc):
         m.reset(x0, trim)
@@ -512,20 +509,17 @@ def test_four_instances_per_warp_kernel_matches_c_oracle(cuda_device, variant, N
 
 
 @pytest.mark.parametrize("variant,N,B,warps", [(12, 20, 301, 3), (17, 10, 77, 2), (12, 8, 9, 1)])
-def test_four_instances_per_warp_kernel_refills_its_groups(cuda_device, variant, N, B, warps, monkeypatch):
+def test_four_instances_per_warp_kernel_refills_its_groups(cuda_device, variant, N, B, warps):
     """Continuous batching of mpcb_qp8.cuh on the GPU: the persistent grid is capped to a few warps
-    (MPCB_QP8_WARPS), so every 8-lane group solves many instances one after the other and is refilled
+    (mpcb_config.qp8_warps), so every 8-lane group solves many instances one after the other and is refilled
     at IPM-iteration boundaries while its neighbours are in the middle of their solves.  Results must
     not depend on that: same status, iteration counts and iterates as the C oracle, bit-identical to
     the same kernel run with one instance per group."""
     P = bo.canonical_problem(N, variant)
     x0, yref = sc.random_setpoints(B, seed=78, nx=P.nx, nu=P.nu)
     trim = sc.hover_trim(P.nu)
-    monkeypatch.setenv("MPCB_QP8_BATCH", "1")
-    monkeypatch.setenv("MPCB_QP8_WARPS", str(warps))
-    few = _mpc(N, B, variant)
-    monkeypatch.delenv("MPCB_QP8_WARPS")
-    wide = _mpc(N, B, variant)
+    few = _mpc(N, B, variant, qp8_batch=1, qp8_warps=warps)
+    wide = _mpc(N, B, variant, qp8_batch=1)
     orc = co.BatchRTI(P, B)
     for m in (few, wide, orc):
         m.reset(x0, trim)
@@ -539,7 +533,7 @@ def test_four_instances_per_warp_kernel_refills_its_groups(cuda_device, variant,
     assert torch.equal(Uf, Uw) and torch.equal(Xf, Xw) and torch.equal(uf, uw) and torch.equal(stf, stw)
 
 
-def test_four_instances_per_warp_kernel_refill_with_infeasible_instances(cuda_device, monkeypatch):
+def test_four_instances_per_warp_kernel_refill_with_infeasible_instances(cuda_device):
     """Random set-points at N = 40 leave ~1.4 % of the linearised QPs infeasible: those
     instances end early with the min-step status in the middle of a warp whose other groups keep
     solving, their iterate must stay untouched, and the group must be refilled like any other.
@@ -548,9 +542,7 @@ def test_four_instances_per_warp_kernel_refill_with_infeasible_instances(cuda_de
     P = bo.canonical_problem(N)
     x0, yref = sc.random_setpoints(B, seed=4567)
     trim = sc.hover_trim()
-    monkeypatch.setenv("MPCB_QP8_BATCH", "1")
-    monkeypatch.setenv("MPCB_QP8_WARPS", "5")
-    mpc = _mpc(N, B)
+    mpc = _mpc(N, B, qp8_batch=1, qp8_warps=5)
     orc = co.BatchRTI(P, B)
     mpc.reset(x0, trim)
     orc.reset(x0, trim)
@@ -650,19 +642,16 @@ def test_mavros_script_configuration(cuda_device):
 
 
 @pytest.mark.parametrize("qp8", [False, True])
-def test_solve_is_cuda_graph_capturable(cuda_device, qp8, monkeypatch):
+def test_solve_is_cuda_graph_capturable(cuda_device, qp8):
     """SURVEY 8b ownership rule: no allocation and no synchronisation inside mpcb_solve, so a control
     loop can capture it in a CUDA graph.  Capture one solve (either QP kernel; the persistent kernel's
     work-counter reset is a memset node), replay it from the same iterate: bit-identical outputs."""
     N, B = 10, 96
-    if qp8:
-        monkeypatch.setenv("MPCB_QP8_BATCH", "1")
-        monkeypatch.setenv("MPCB_QP8_WARPS", "7")
     x0, yref = sc.random_setpoints(B, seed=5)
     x0 = torch.as_tensor(x0, device="cuda")
     yref = torch.as_tensor(yref, device="cuda")
     trim = torch.as_tensor(sc.hover_trim(), device="cuda")
-    mpc = _mpc(N, B)
+    mpc = _mpc(N, B, **(dict(qp8_batch=1, qp8_warps=7) if qp8 else {}))
     mpc.reset(x0, trim)
     u_e, X_e, U_e, st_e = mpc.solve(x0, yref)
     torch.cuda.synchronize()
@@ -710,7 +699,7 @@ def test_full_size_config5_sample_against_oracle(cuda_device, variant):
 
 
 @pytest.mark.parametrize("B,qp8", [(96, False), (200, True)])
-def test_quat13_variant_matches_oracle(cuda_device, B, qp8, monkeypatch):
+def test_quat13_variant_matches_oracle(cuda_device, B, qp8):
     """QUAT13: the 12-state quadrotor with its attitude as a unit quaternion, dynamics
     built on the quaternion algebra of the reference's utils/MathUtils.py.  No reference model uses it,
     so the checks are: linearisation, two closed-loop solves and the plant step against the oracles
@@ -719,10 +708,7 @@ def test_quat13_variant_matches_oracle(cuda_device, B, qp8, monkeypatch):
     P = bo.canonical_problem(N, 13)
     x0, yref = sc.random_setpoints(B, seed=91, nx=13, nu=4)
     trim = sc.hover_trim(4)
-    if qp8:
-        monkeypatch.setenv("MPCB_QP8_BATCH", "1")
-        monkeypatch.setenv("MPCB_QP8_WARPS", "9")
-    mpc = _mpc(N, B, 13)
+    mpc = _mpc(N, B, 13, **(dict(qp8_batch=1, qp8_warps=9) if qp8 else {}))
     orc = co.BatchRTI(P, B)
     mpc.reset(x0, trim)
     orc.reset(x0, trim)
@@ -749,18 +735,15 @@ def test_quat13_variant_matches_oracle(cuda_device, B, qp8, monkeypatch):
 
 
 @pytest.mark.parametrize("qp8", [False, True])
-def test_nan_and_inf_inputs_are_reported_per_instance(cuda_device, qp8, monkeypatch):
+def test_nan_and_inf_inputs_are_reported_per_instance(cuda_device, qp8):
     """A NaN in one instance's x0, an infinite set-point in another's and an x0 a kilometre outside the arena
     in a third: statuses 1 / 1 / 3 (NaN, NaN, min-step) as the C oracle reports them, their iterates untouched,
     every other instance of the warp / batch solved to the usual parity."""
     N, B = 10, 37
-    if qp8:
-        monkeypatch.setenv("MPCB_QP8_BATCH", "1")
-        monkeypatch.setenv("MPCB_QP8_WARPS", "2")
     P = bo.canonical_problem(N)
     x0, yref = sc.random_setpoints(B, seed=3)
     trim = sc.hover_trim()
-    mpc = _mpc(N, B)
+    mpc = _mpc(N, B, **(dict(qp8_batch=1, qp8_warps=2) if qp8 else {}))
     orc = co.BatchRTI(P, B)
     mpc.reset(x0, trim)
     orc.reset(x0, trim)

@@ -218,3 +218,61 @@ def test_emulated_kernel_infeasible_instance_keeps_the_checkers_status():
     c = co.BatchRTI(P, 1, nthreads=1)
     _, _, _, stc = c.solve(x0[i:i + 1], yref[i], p)
     assert stc[0] != 0 and st == stc[0] and it == c.iters[0]
+
+
+@pytest.mark.parametrize("variant", [17, 12])
+def test_emulated_kernel_strict_reference_semantics_match_both_oracles(variant):
+    """mpcb_config.strict_reference: the stopping test uses the residual norms the backward sweep evaluates explicitly on
+    the iterate (stationarity included), as HPIPM's does, instead of their extrapolated values.  The strict instantiation
+    of qp_solve_warp (host emulation), the C oracle (Riccati) and the NumPy oracle (dense KKT) must stop after the same
+    number of iterations with the same status and the same iterate; the default rule set must reach the same primal
+    solution (it may stop an iteration earlier or later)."""
+    N = 10
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.random_setpoints(3, seed=77, nx=P.nx, nu=P.nu)
+    p = bo.default_params()
+    for i in range(3):
+        X = np.repeat(x0[i][None], N + 1, axis=0).copy()
+        U = np.tile(sc.hover_trim(P.nu), (N, 1)).copy()
+        Xd, Ud = X.copy(), U.copy()
+        st, it, _, _ = eb.rti_solve(P, X, U, x0[i], yref[i], p, strict=True)
+        c = co.BatchRTI(P, 1, nthreads=1, strict=True)
+        c.reset(x0[i:i + 1], sc.hover_trim(P.nu))
+        _, Xc, Uc, stc = c.solve(x0[i:i + 1], yref[i], p)
+        o = bo.RTIOracle(P, strict=True)
+        o.reset(x0[i], sc.hover_trim(P.nu))
+        _, Xo, Uo, sto = o.solve(x0[i], yref[i])
+        assert c.o.ipm_max_iter == 500 and c.o.strict == 1
+        assert st == stc[0] == sto and it == c.iters[0] == o.last[1].iters, (st, stc, sto, it, c.iters, o.last[1].iters)
+        if st in (0, 2):  # the step is applied on success and, under the reference's semantics, on max-iter
+            assert np.abs(Xc[0] - X).max() < 1e-8 and np.abs(Uc[0] - U).max() < 1e-7
+            assert np.abs(Xo - X).max() < 1e-8 and np.abs(Uo - U).max() < 1e-7
+        # the explicit stationarity norm of the strict solve is what the test saw
+        if st == 0:
+            assert o.last[1].res[4] <= 1e-6 and o.last[1].res[5] <= 1e-8 and o.last[1].res[6] <= 1e-8
+        std, itd, _, _ = eb.rti_solve(P, Xd, Ud, x0[i], yref[i], p)
+        if st == 0 and std == 0:
+            assert abs(it - itd) <= 2
+            assert np.abs(Xd - X).max() < 1e-6 and np.abs(Ud[:, :4] - U[:, :4]).max() < 1e-5
+
+
+def test_strict_reference_applies_the_last_iterate_on_max_iter():
+    """acados takes HPIPM's last iterate when the QP solver returns max-iter; the default rule set leaves the iterate
+    untouched on any failure.  A cap of 4 interior-point iterations forces status 2 in both modes."""
+    N = 8
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(1, seed=5)
+    p = bo.default_params()
+    X0 = np.repeat(x0[0][None], N + 1, axis=0)
+    U0 = np.tile(sc.hover_trim(), (N, 1))
+    X, U = X0.copy(), U0.copy()
+    st, it, _, _ = eb.rti_solve(P, X, U, x0[0], yref[0], p, max_iter=4)
+    assert st == 2 and it == 4 and np.array_equal(X, X0) and np.array_equal(U, U0)
+    Xs, Us = X0.copy(), U0.copy()
+    st, it, _, _ = eb.rti_solve(P, Xs, Us, x0[0], yref[0], p, max_iter=4, strict=True)
+    c = co.BatchRTI(P, 1, nthreads=1, strict=True, max_iter=4)
+    c.reset(x0, sc.hover_trim())
+    _, Xc, Uc, stc = c.solve(x0, yref[0], p)
+    assert st == stc[0] == 2 and it == c.iters[0] == 4
+    assert np.abs(Us - U0).max() > 1e-3  # the step was taken
+    assert np.abs(Xc[0] - Xs).max() < 1e-9 and np.abs(Uc[0] - Us).max() < 1e-8

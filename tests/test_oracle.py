@@ -299,3 +299,81 @@ def test_quat13_model_is_the_euler_model_in_quaternion_coordinates():
         uo, Xo, Uo, so = o.solve(x0[i], yref[i])
         assert so == st[i] == 0
         assert np.abs(Uo - U[i]).max() < 1e-7 and np.abs(Xo - X[i]).max() < 1e-8
+
+
+def test_sqp_to_convergence_c_oracle_matches_numpy_oracle():
+    """SQP to convergence with the options the reference's dump carries (nlp_solver_tol_* = 1e-6,
+    nlp_solver_max_iter = 100, acados_ocp_blasterModel.json solver_options).  The C restatement (Riccati IPM) and the
+    NumPy one (dense KKT) run the same loop -- linearise, NLP residuals with the last QP's multipliers, stop or solve the
+    QP and take the full step -- and must agree on the number of QPs, the status and the converged iterate; the
+    converged iterate must satisfy the NLP KKT conditions (the residuals are the certificate)."""
+    from oracle import c_oracle as co
+    from mpc_blaster_b200 import scenarios as sc
+    N = 10
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(3, seed=11)
+    trim = sc.hover_trim()
+    c = co.BatchRTI(P, 3, nthreads=1)
+    c.reset(x0, trim)
+    u0, Xc, Uc, st, n_qp, qp_it, res = c.sqp_solve(x0, yref, max_iter=100, tol=1e-6)
+    assert (st == 0).all() and (n_qp >= 2).all() and (n_qp < 30).all() and (res <= 1e-6).all(), (st, n_qp, res)
+    for i in range(3):
+        o = bo.RTIOracle(P)
+        o.reset(x0[i], trim)
+        _, Xo, Uo, sto, n_o, it_o, res_o = o.sqp_solve(x0[i], yref[i], max_iter=100, tol=1e-6)
+        assert sto == 0 and n_o == n_qp[i] and it_o == qp_it[i], (i, sto, n_o, n_qp[i], it_o, qp_it[i])
+        assert np.abs(Xo - Xc[i]).max() < 1e-6 and np.abs(Uo - Uc[i]).max() < 1e-6
+        assert max(res_o) <= 1e-6 and np.abs(np.array(res_o) - res[i]).max() < 1e-7
+    # an iteration cap below what convergence needs: status 2, exactly that many QPs, residuals above the tolerance
+    c.reset(x0, trim)
+    _, _, _, st2, n2, _, res2 = c.sqp_solve(x0, yref, max_iter=2, tol=1e-6)
+    assert (st2 == 2).all() and (n2 == 2).all() and (res2.max(axis=1) > 1e-6).all()
+    # one SQP iteration from the same start is the RTI step
+    c.reset(x0, trim)
+    _, X1, U1, _, _, _, _ = c.sqp_solve(x0, yref, max_iter=1, tol=0.0)
+    r = co.BatchRTI(P, 3, nthreads=1)
+    r.reset(x0, trim)
+    _, Xr, Ur, _ = r.solve(x0, yref)
+    assert np.array_equal(X1, Xr) and np.array_equal(U1, Ur)
+
+
+def test_explicit_kkt_residual_evaluation_agrees_with_the_dense_certificate():
+    """oracle.explicit_kkt_residuals evaluates the KKT residuals of a stage-ordered iterate (the layout mpcb_debug_qp
+    exports from the GPU); on the NumPy oracle's own solution, re-packed into that layout, it must reproduce the dense
+    certificate (kkt_certificate) of the same point -- so the GPU test's checker is itself checked."""
+    from mpc_blaster_b200 import scenarios as sc
+    N = 6
+    P = bo.canonical_problem(N)
+    x0, yref = sc.random_setpoints(1, seed=3)
+    o = bo.RTIOracle(P)
+    o.reset(x0[0], sc.hover_trim())
+    o.solve(x0[0], yref[0])
+    qp, r = o.last
+    H, g, C, c, lb, ub = bo.qp_to_dense(qp)
+    cert = bo.kkt_certificate(H, g, C, c, lb, ub, r.z, r.pi, r.lam_l, r.lam_u)
+    nx, nu = P.nx, P.nu
+    nz = nx + nu
+    z = np.zeros((1, N + 1, nz)); pi = np.zeros((1, N + 1, nx)); ll = np.zeros_like(z); lu = np.zeros_like(z)
+    lbs = np.full_like(z, -np.inf); ubs = np.full_like(z, np.inf); gs = np.zeros_like(z)
+    zz, l_l, l_u = r.z.reshape(N, nz), r.lam_l.reshape(N, nz), r.lam_u.reshape(N, nz)
+    lbd, ubd, gd = lb.reshape(N, nz), ub.reshape(N, nz), g.reshape(N, nz)
+    z[0, 0, nu:] = qp.dx0
+    BAt = np.zeros((1, N, nz, nx)); bb = np.zeros((1, N, nx))
+    for k in range(N):
+        for dst, src in ((z, zz), (ll, l_l), (lu, l_u), (lbs, lbd), (ubs, ubd), (gs, gd)):
+            dst[0, k, :nu] = src[k, :nu]
+            dst[0, k + 1, nu:] = src[k, nu:]
+        pi[0, k + 1] = -r.pi[k * nx:(k + 1) * nx]  # the dense ordering carries the opposite sign of the Riccati one
+        BAt[0, k, :nu], BAt[0, k, nu:], bb[0, k] = qp.B[k].T, qp.A[k].T, qp.b[k]
+    fin_l, fin_u = np.isfinite(lbs), np.isfinite(ubs)
+    tl = np.where(fin_l, z - np.where(fin_l, lbs, 0.0), 1.0)
+    tu = np.where(fin_u, np.where(fin_u, ubs, 0.0) - z, 1.0)
+    out = bo.explicit_kkt_residuals(P, z, pi, tl, tu, ll, lu, lbs, ubs, gs, BAt, bb)
+    assert abs(out["stat"][0] - cert["stat"]) < 1e-15 and abs(out["comp"][0] - cert["comp"]) < 1e-18
+    assert out["eq"][0] < 1e-14 and out["viol"][0] == 0.0 and out["ineq"][0] == 0.0 and out["neg"][0] <= 0.0
+    assert out["stat_comp"].shape == (1, nz) and out["stat_comp"].max() == out["stat"][0]
+    # a perturbed multiplier shows up in the stationarity norm of exactly its component
+    ll2 = ll.copy()
+    ll2[0, 2, 1] += 1e-3
+    out2 = bo.explicit_kkt_residuals(P, z, pi, tl, tu, ll2, lu, lbs, ubs, gs, BAt, bb)
+    assert abs(out2["stat_comp"][0, 1] - 1e-3) < 1e-9 and out2["stat_comp"][0, 0] == out["stat_comp"][0, 0]

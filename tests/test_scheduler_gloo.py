@@ -63,3 +63,22 @@ def test_two_rank_sharded_solve_equals_single_process(tmp_path):
     u0, _, _, st = co.BatchRTI(P, B, nthreads=1).solve(x0, yref)
     assert np.array_equal(np.load(tmp_path / "u0.npy"), u0)
     assert np.array_equal(np.load(tmp_path / "st.npy"), st)
+
+
+def test_shard_treats_one_dimensional_tensors_as_shared_whatever_their_length():
+    """A shared yref[ny] with B == ny (23) or a shared p[25] with B == 25 must not be sliced; per-instance tensors lead
+    with B and anything else is an error (the solver's own shape rule, BlasterMPC._mode)."""
+    import pytest
+    import torch
+    from mpc_blaster_b200.scheduler import shard
+    for B in (23, 25, 17):
+        y = torch.arange(23.0)
+        p = torch.arange(25.0)
+        assert shard(y, B, 1, 2) is y and shard(p, B, 1, 2) is p
+        x0 = torch.zeros(B, 17)
+        lo = B // 2 + (B % 2)
+        assert shard(x0, B, 1, 2).shape == (B - lo, 17)
+        assert shard(torch.zeros(B, 21, 23), B, 0, 2).shape == (lo, 21, 23)
+    with pytest.raises(ValueError):
+        shard(torch.zeros(5, 23), 23, 0, 2)
+    assert shard(None, 8, 0, 2) is None

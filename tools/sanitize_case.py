@@ -22,12 +22,10 @@ for variant in (17, 12):
     torch.cuda.synchronize()
     print(variant, st.tolist(), mpc.iters.tolist(), float(c.sum()))
 # four-instances-per-warp kernel, one persistent warp: its groups are refilled from the work counter
-os.environ["MPCB_QP8_BATCH"] = "1"
-os.environ["MPCB_QP8_WARPS"] = "1"
 for variant in (17, 12):
     nx, nu = (17, 6) if variant == 17 else (12, 4)
     x0, yref = sc.random_setpoints(11, seed=5, nx=nx, nu=nu)
-    mpc = BlasterMPC.canonical(N=5, batch=11, variant=variant)
+    mpc = BlasterMPC.canonical(N=5, batch=11, variant=variant, qp8_batch=1, qp8_warps=1)
     mpc.reset(x0, sc.hover_trim(nu))
     u0, X, U, st = mpc.solve(x0, yref)
     torch.cuda.synchronize()

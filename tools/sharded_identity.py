@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Sharded == unsharded on GPUs (distributed row; run by tests/test_gpu_round2.py and by hand:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/sharded_identity.py
+
+Every rank solves its contiguous shard of one global batch through ``ShardedSolve`` (one process per GPU, NCCL
+all-gather of u0 / status -- the only collective of the job); rank 0 also solves the whole batch on its own GPU.  The
+gathered result must equal the unsharded one bit for bit, over two control steps (the second from the warm-started
+iterate each shard keeps on its GPU).  With fewer GPUs than ranks the ranks share GPU 0 and gather over gloo."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpc_blaster_b200 import BlasterMPC, scenarios as sc  # noqa: E402
+from mpc_blaster_b200.scheduler import ShardedSolve, shard_range  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=1000)
+    ap.add_argument("--horizon", type=int, default=20)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    ngpu = torch.cuda.device_count()
+    nccl = ngpu >= world
+    dev = torch.device("cuda", local if nccl else 0)
+    torch.cuda.set_device(dev)
+    if nccl:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
+    B, N = a.batch, a.horizon
+    x0_h, yref_h = sc.random_setpoints(B, seed=99)
+    trim = torch.as_tensor(sc.hover_trim(), device=dev)
+    lo, hi = shard_range(B, rank, world)
+    mpc = BlasterMPC.canonical(N=N, batch=hi - lo, device=dev)
+    mpc.reset(torch.as_tensor(x0_h[lo:hi], device=dev), trim)
+    gdev = dev if nccl else torch.device("cpu")
+
+    def solve_fn(x0, yref, p):
+        u0, X, U, st = mpc.solve(x0.to(dev), yref.to(dev), p, want_traj=False)
+        return u0.to(gdev), X, U, st.to(gdev)
+
+    job = ShardedSolve(solve_fn, B)
+    x0 = torch.as_tensor(x0_h, device=gdev)
+    yref = torch.as_tensor(yref_h, device=gdev)
+    outs = []
+    for step in range(2):
+        u0, st = job.solve(x0, yref)
+        outs.append((u0.cpu(), st.cpu()))
+        # next control step: every instance moves to the state its own u0 gives (same plant on every rank)
+        xs = mpc.step_plant(x0[lo:hi].to(dev), u0[lo:hi].to(dev))
+        from mpc_blaster_b200.scheduler import gather_batch
+        x0 = gather_batch(xs.to(gdev), B)
+    ok = True
+    rep = None
+    if rank == 0:
+        whole = BlasterMPC.canonical(N=N, batch=B, device=dev)
+        whole.reset(torch.as_tensor(x0_h, device=dev), trim)
+        xw = torch.as_tensor(x0_h, device=dev)
+        conv = 1.0
+        for step in range(2):
+            uw, _, _, sw = whole.solve(xw, torch.as_tensor(yref_h, device=dev), want_traj=False)
+            ok = ok and torch.equal(uw.cpu(), outs[step][0]) and torch.equal(sw.cpu(), outs[step][1])
+            conv = min(conv, float((sw == 0).double().mean()))
+            xw = whole.step_plant(xw, uw)
+        rep = {"identical": bool(ok), "world": world, "backend": "nccl" if nccl else "gloo (ranks share one GPU)", "gpus": ngpu,
+               "global_batch": B, "horizon": N, "control_steps": 2, "converged_frac": conv,
+               "shards": [list(shard_range(B, g, world)) for g in range(world)]}
+        print(json.dumps(rep), flush=True)
+        out = os.environ.get("MPCB_IDENTITY_OUT")
+        if out:
+            with open(out, "w") as f:
+                json.dump(rep, f)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
