@@ -21,6 +21,10 @@
 //   Per IPM iteration the stage matrices are read four times and L is written once.
 #pragma once
 #include "mpcb_common.cuh"
+#ifdef MPCB_HOST_EMU
+#include <cstdio>
+#include <cstdlib>
+#endif
 
 namespace mpcb {
 
@@ -361,6 +365,92 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
     imax_out = warp_max(imax);
     acc1_out = warp_sum(acc1);
     acc2_out = warp_sum(acc2);
+}
+
+// Forward sweep of an iterative-refinement increment (STRICT instantiation only; plain global loads, no prefetch
+// pipeline): the backward increment sweep left [d lvec_k; d p_k] in the c1 slot of every record; this computes the step
+// increment (ddu_k = -Luu^{-T}(d lvec_k + Lxu' ddx_k), ddx_{k+1} = [B A] ddz_k, ddpi_{k+1} = P_{k+1} ddx_{k+1} + d p_{k+1}),
+// ADDS it to dz / dpi in the records and redoes the box step-length computation of the corrected step.
+template <int NX, int NU, typename T, int NSLOT>
+MPCB_DEV void refine_forward(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__restrict__ ws, T sigmu, T &imax_out)
+{
+    using L = Layout<NX, NU>;
+    constexpr int NZ = L::NZ;
+    const int lane = lane_id();
+    const int N = P.N;
+    T imax = T(0);
+    if (lane < NX) sm.cDx[lane] = T(0);
+    warp_sync();
+    for (int k = 0; k < N; k++) {
+        T *wk = ws + (size_t)k * L::STAGE;
+        T yy = T(0);
+        if (lane < NU) {
+            T a = wk[L::O_C1 + lane];
+            MPCB_UNROLL4
+            for (int i = 0; i < NX; i++) a += wk[L::O_LU + lane * L::NZP + NU + i] * sm.cDx[i];
+            yy = -a;
+        }
+        T du = T(0);
+        MPCB_UNROLL
+        for (int i = NU - 1; i >= 0; i--) {
+            const T dui = warp_shfl(yy, i) * wk[L::O_INVD + i];
+            if (lane == i) du = dui;
+            if (lane < i) yy -= wk[L::O_LU + lane * L::NZP + i] * dui;
+        }
+        T ddz = T(0);
+        if (lane < NU) ddz = du;
+        else if (lane < NZ) ddz = sm.cDx[lane - NU];
+        T dz = T(0);
+        if (lane < NZ) {
+            dz = wk[L::O_DZ + lane] + ddz;
+            wk[L::O_DZ + lane] = dz;
+            sm.sDz[lane] = ddz;
+        }
+        if (var_kind<NX, NU>(k, lane, N).hasb) {
+            const T z = wk[L::O_Z + lane], tl = wk[L::O_TL + lane], tu = wk[L::O_TU + lane];
+            const T ll = wk[L::O_LL + lane], lu = wk[L::O_LUP + lane], lb = wk[L::O_LB + lane], ub = wk[L::O_UB + lane];
+            const T itl = fast_rcp(tl), itu = fast_rcp(tu);
+            T rml = ll * tl, rmu = lu * tu;
+            const BoxStep<T> a = box_step(z, wk[L::O_DZA + lane], lb, ub, tl, tu, ll, lu, rml, rmu, itl, itu);
+            rml += a.dll * a.dtl - sigmu;
+            rmu += a.dlu * a.dtu - sigmu;
+            const BoxStep<T> b = box_step(z, dz, lb, ub, tl, tu, ll, lu, rml, rmu, itl, itu);
+            imax = fmax(imax, fmax(fmax(inv_ratio(b.dtl, itl), inv_ratio(b.dtu, itu)),
+                                   fmax(inv_ratio(b.dll, fast_rcp(ll)), inv_ratio(b.dlu, fast_rcp(lu)))));
+        }
+        warp_sync();
+        // ddx_{k+1} = [B A] ddz_k (the dynamics residual of the first solve is zero to rounding by construction)
+        if (lane < NX) {
+            T a0 = T(0), a1 = T(0);
+            MPCB_UNROLL4
+            for (int j = 0; j + 1 < NZ; j += 2) {
+                a0 += wk[L::O_BAT + j * L::LDB + lane] * sm.sDz[j];
+                a1 += wk[L::O_BAT + (j + 1) * L::LDB + lane] * sm.sDz[j + 1];
+            }
+            if (NZ & 1) a0 += wk[L::O_BAT + (NZ - 1) * L::LDB + lane] * sm.sDz[NZ - 1];
+            const T dxn = a0 + a1;
+            sm.cDx[lane] = dxn;
+            sm.sRb[lane] = dxn;
+        }
+        warp_sync();
+        // ddpi_{k+1} = Lxx_{k+1} (Lxx_{k+1}' ddx_{k+1}) + d p_{k+1}
+        const int c = lane < NX ? lane : 0;
+        const T *Lx = wk + L::STAGE + L::O_LXX;
+        T t1 = T(0);
+        MPCB_UNROLL4
+        for (int j = 0; j < NX; j++) t1 += Lx[j * NX + c] * sm.sRb[j];
+        if (lane < NX) sm.sT1[lane] = t1;
+        warp_sync();
+        T t2 = wk[L::STAGE + L::O_C1 + NU + c];
+        MPCB_UNROLL4
+        for (int j = 0; j < NX; j++) t2 += Lx[c * NX + j] * sm.sT1[j];
+        if (lane < NX) wk[L::STAGE + L::O_DPI + lane] += t2;
+        warp_sync();
+    }
+    if (lane >= NU && lane < NZ) ws[(size_t)N * L::STAGE + L::O_DZ + lane] += sm.cDx[lane - NU];
+    pipe_fence();
+    warp_sync();
+    imax_out = warp_max(imax);
 }
 
 // The whole QP solve for one instance.  On return the persistent iterate Xi/Ui has taken
@@ -733,6 +823,9 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
         if (STRICT) {
             // reference semantics: test the residuals S1 has just evaluated on this iterate (before using the factorisation)
             xg = warp_max(xg); xb = warp_max(xb); xd = warp_max(xd);
+#ifdef MPCB_HOST_EMU
+            if (getenv("MPCB_EMU_DEBUG") && lane == 0) fprintf(stderr, "emu it %d res_g %.3e res_b %.3e res_d %.3e comp %.3e mu %.3e\n", it, (double)xg, (double)xb, (double)xd, (double)comp, (double)mu);
+#endif
             if (!(xg == xg) || !(xb == xb)) { status = ST_NAN; break; }
             if (xg <= (T)P.tol_stat && xb <= (T)P.tol_eq && xd <= (T)P.tol_ineq && comp <= (T)P.tol_comp) { status = ST_OK; break; }
         }
@@ -752,8 +845,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
         }
 
         // ================= S3: backward sweep for the corrector increment (delta form)
-        // record k: [BAt | Lu | invd | lvec] and [c1 c2]; pv_k is read-modify-written in global memory
-        {
+        // record k: [BAt | Lu | invd | lvec] and [c1 c2]; pv_k is read-modify-written in global memory.
+        // REF = 1 (STRICT only): the same backward sweep for an iterative-refinement increment -- the right-hand side is the
+        // residual rho the flat pass below left in the c1 slot (every row, and a terminal-stage part = the increment of p_N).
+        auto corrector_sweep = [&](auto REF) {
+            constexpr bool REFINE = decltype(REF)::value != 0;
             constexpr int RUN1 = L::O_RB;
             auto fetch3 = [&](int k, int half) {
                 const T *wk = ws + (size_t)k * L::STAGE;
@@ -762,7 +858,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 pipe_copy(pipe, half, sm.slot[half] + L::O_C1, wk + L::O_C1, 2 * L::NZP);
             };
             if (NSLOT == 2) fetch3(N - 1, (N - 1) & 1);
-            if (lane < NX) sm.cPv[lane] = T(0);
+            if (lane < NX) sm.cPv[lane] = REFINE ? ws[(size_t)N * L::STAGE + L::O_C1 + NU + lane] : T(0);  // increment of p_N
             for (int k = N - 1; k >= 0; k--) {
                 T *wk = ws + (size_t)k * L::STAGE;
                 const int half = (NSLOT == 2) ? (k & 1) : 0;
@@ -782,7 +878,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 warp_sync();
                 const int jr = lane < NZ ? lane : 0;
                 const VarKind vk = var_kind<NX, NU>(k, lane, N);
-                T l0 = vk.hasb ? s[L::O_C1 + lane] - sigmu * s[L::O_C2 + lane] : T(0), l1 = T(0);
+                T l0 = REFINE ? (lane < NZ ? s[L::O_C1 + jr] : T(0)) : (vk.hasb ? s[L::O_C1 + lane] - sigmu * s[L::O_C2 + lane] : T(0)), l1 = T(0);
                 MPCB_UNROLL
                 for (int c = 0; c + 1 < NX; c += 2) {
                     l0 += s[L::O_BAT + jr * L::LDB + c] * sm.cPv[c];
@@ -794,13 +890,21 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 for (int c = 0; c < NU; c++) { Lu[c] = s[L::O_LU + c * L::NZP + jr]; invd[c] = s[L::O_INVD + c]; }
                 const T l = fwd_subst<NU, T>((lane < NZ) ? l0 + l1 : T(0), Lu, invd, NZ);
                 warp_sync();
-                if (lane < NU) wk[L::O_LVEC + lane] = s[L::O_LVEC + lane] + l;
-                else if (lane < NZ) { wk[L::O_PV + lane - NU] = pv_old + l; sm.cPv[lane - NU] = l; }
+                if (REFINE) {
+                    // the increment stays separate ([d lvec; d p_k] replaces rho in the c1 slot): refine_forward adds the
+                    // step it yields to dz / dpi, so the rounding of the first solve is corrected, not repeated
+                    if (lane < NZ) wk[L::O_C1 + lane] = l;
+                    if (lane >= NU && lane < NZ) sm.cPv[lane - NU] = l;
+                } else {
+                    if (lane < NU) wk[L::O_LVEC + lane] = s[L::O_LVEC + lane] + l;
+                    else if (lane < NZ) { wk[L::O_PV + lane - NU] = pv_old + l; sm.cPv[lane - NU] = l; }
+                }
                 warp_sync();
             }
             pipe_fence();
             warp_sync();
-        }
+        };
+        corrector_sweep(IntC<0>{});
 
         // ================= S4: forward sweep, full predictor-corrector step (+ dpi, + step length)
         T alpha;
@@ -808,6 +912,55 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             T imax, d1, d2;
             forward_sweep<NX, NU, T, NSLOT, true>(P, sm, pipe, ws, sigmu, imax, d1, d2);
             // alpha = min(1, max(0.995, 1 - mu_aff) * alpha_max)
+            const T tau = fmax(T(0.995), T(1) - mu_aff);
+            alpha = (imax > tau) ? tau / imax : T(1);
+        }
+        if (STRICT) {
+            // ================= R: one step of iterative refinement on the step just computed (HPIPM: itref_corr_max).
+            // The residual of the stationarity rows of the reduced Newton system,
+            //   rho_k = Hd_k dz_k + q_k + [B A]' dpi_{k+1} - [dpi_k]_x,   q_k = the corrector's right-hand side,
+            // evaluated from the data in one flat pass (the dynamics rows hold to rounding by construction of the forward
+            // sweep), goes through the same factorisation as a delta (S3 with REF = 1) and the forward sweep is redone.
+            // With active state bounds the Riccati solve alone leaves the explicit stationarity norm at 1e-5 .. 1e-3
+            // (in the multipliers; the primal step is already accurate); with this step the explicit norms reach
+            // HPIPM's tolerances after the same number of iterations the extrapolated test predicts.
+            MPCB_NOUNROLL
+            for (int k = 0; k <= N; k++) {
+                T *wk = ws + (size_t)k * L::STAGE;
+                const VarKind vk = var_kind<NX, NU>(k, lane, N);
+                T rho = T(0);
+                if (vk.var) {
+                    const T H0 = (k < N) ? H0s : H0N;
+                    const T z = wk[L::O_Z + lane], dz = wk[L::O_DZ + lane];
+                    T r = H0 * z + wk[L::O_G + lane], Hd = H0, dsum = T(0);
+                    if (k < N) {
+                        MPCB_UNROLL4
+                        for (int c = 0; c < NX; c++) {
+                            const T a = wk[L::O_BAT + lane * L::LDB + c];
+                            r += a * wk[L::STAGE + L::O_PI + c];
+                            dsum += a * wk[L::STAGE + L::O_DPI + c];
+                        }
+                    }
+                    if (lane >= NU) { r -= wk[L::O_PI + lane - NU]; dsum -= wk[L::O_DPI + lane - NU]; }
+                    if (vk.hasb) {
+                        const T tl = wk[L::O_TL + lane], tu = wk[L::O_TU + lane], ll = wk[L::O_LL + lane], lu = wk[L::O_LUP + lane];
+                        const T itl = T(1) / tl, itu = T(1) / tu;
+                        const T rdl = z - wk[L::O_LB + lane] - tl, rdu = wk[L::O_UB + lane] - z - tu;
+                        Hd += ll * itl + lu * itu;
+                        r += ll * rdl * itl - lu * rdu * itu + (wk[L::O_C1 + lane] - sigmu * wk[L::O_C2 + lane]);
+                    }
+                    rho = Hd * dz + r + dsum;
+                }
+                if (lane < NZ) { wk[L::O_C1 + lane] = rho; wk[L::O_C2 + lane] = T(0); }
+#ifdef MPCB_HOST_EMU
+                if (getenv("MPCB_EMU_DEBUG")) { const T m_ = warp_max(fabs(rho)); if (lane == 0 && m_ > 1e-9) fprintf(stderr, "   emu rho stage %d: %.3e\n", k, (double)m_); }
+#endif
+            }
+            pipe_fence();
+            warp_sync();
+            corrector_sweep(IntC<1>{});
+            T imax;
+            refine_forward<NX, NU, T, NSLOT>(P, sm, ws, sigmu, imax);
             const T tau = fmax(T(0.995), T(1) - mu_aff);
             alpha = (imax > tau) ? tau / imax : T(1);
         }

