@@ -128,7 +128,10 @@ int mpcb_solve_host(mpcb_handle *h, const double *x0, const double *yref, int yr
  *   tol != NULL: tol[4] = {stat, eq, ineq, comp}.  Per instance, acados' SQP loop: linearise; evaluate the NLP residuals
  *     (inf-norms of the Lagrangian gradient with the last QP's multipliers, of the dynamics defect, of the bound
  *     violation and of the complementarity products); stop when all four are within tolerance; otherwise solve the QP and
- *     take the full step; at most max_iter QPs.  Finished instances are skipped by the kernels.  status[B]: 0 converged,
+ *     take the full step; at most max_iter QPs.  Finished instances are skipped by the kernels.  The QPs of this mode are
+ *     always solved with the reference-semantics rule set (strict_reference: explicit residual norms and one step of
+ *     iterative refinement), whatever the handle's setting: the Lagrangian-gradient test needs the QP's multipliers to
+ *     1e-6, which the default rule set does not deliver for active bounds.  status[B]: 0 converged,
  *     2 max_iter reached, 4 a QP failed (its own status was not 0), 1 NaN; iters[B]: interior-point iterations summed
  *     over the QPs; sqp_iters[B]: QPs solved; nlp_res[B,4]: the last evaluated residuals (the final iterate's).
  *   tol == NULL: exactly max_iter SQP iterations without a residual test; status / iters are those of the last QP.

@@ -95,15 +95,14 @@ template <int NX, int NU>
 __global__ void __launch_bounds__(32) qp8_kernel(const __grid_constant__ Params P, double *__restrict__ X, double *__restrict__ U,
                                                  const double *__restrict__ x0, const double *__restrict__ yref, int yref_mode,
                                                  double *__restrict__ ws, double *__restrict__ u0, int32_t *__restrict__ status,
-                                                 int32_t *__restrict__ iters, int inst0, int B, unsigned *__restrict__ next,
-                                                 const int32_t *__restrict__ skip)
+                                                 int32_t *__restrict__ iters, int inst0, int B, unsigned *__restrict__ next)
 {
     __shared__ Qp8Smem<NX, NU> sm;
     Qp8Batch job;
     job.X = X; job.U = U; job.x0 = x0; job.yref = yref;
     job.yref_stride = yref_mode == MPCB_PER_INSTANCE ? (size_t)(NX + NU) : yref_mode == MPCB_PER_STAGE ? (size_t)(P.N + 1) * (NX + NU) : 0;
     job.yps = yref_mode == MPCB_PER_STAGE;
-    job.ws = ws; job.u0 = u0; job.status = status; job.iters = iters; job.inst0 = inst0; job.B = B; job.next = next; job.skip = skip;
+    job.ws = ws; job.u0 = u0; job.status = status; job.iters = iters; job.inst0 = inst0; job.B = B; job.next = next;
     qp8_solve_queue<NX, NU>(P, sm, job);
 }
 
@@ -521,6 +520,10 @@ int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, in
                         double *u0, int32_t *status, int32_t *iters, int B, cudaStream_t s, const SqpState *sqp = nullptr,
                         int sqp_it = 0, bool sqp_eval_only = false)
 {
+    // SQP to convergence tests the Lagrangian gradient with the QP's multipliers at 1e-6: that needs the refined solve of
+    // the reference-semantics instantiation (the default rule set leaves up to ~1e-3 in the multipliers of active bounds)
+    Params P = h->P;
+    if (sqp) P.strict = 1;
     static_assert(sizeof(QpSmem<NX, NU, double, 2>) * kWPB <= 48 * 1024, "static shared memory limit");
     using L = Layout<NX, NU>;
     const size_t smem = 0;
@@ -531,37 +534,37 @@ int launch_solve_chunks(mpcb_handle *h, const double *x0, const double *yref, in
         const unsigned g1 = (unsigned)((warps * 32 + 127) / 128);
         const bool prof = h->profile && i0 == 0;
         if (prof) cudaEventRecord(h->ev[0], s);
-        linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(h->P, h->X, h->U, p, p_mode, h->ws, i0, nb, skip);
+        linearize_kernel<NX, NU><<<g1, 128, 0, s>>>(P, h->X, h->U, p, p_mode, h->ws, i0, nb, skip);
         g_launches += 1;
         if (sqp) {
-            nlp_res_kernel<NX, NU><<<(unsigned)(((long long)nb * 32 + 127) / 128), 128, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, *sqp,
+            nlp_res_kernel<NX, NU><<<(unsigned)(((long long)nb * 32 + 127) / 128), 128, 0, s>>>(P, h->X, h->U, x0, yref, yref_mode, h->ws, *sqp,
                                                                                              sqp_it, u0, i0, nb);
             g_launches += 1;
             if (sqp_eval_only) continue;
         }
         if (prof) cudaEventRecord(h->ev[1], s);
-        if (h->P.strict)
+        if (P.strict)
             // reference semantics (explicit residual norms, no divergence exit): the one-instance latency kernel, any batch
-            qp_kernel<NX, NU, kWPB, 2, 1, true><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+            qp_kernel<NX, NU, kWPB, 2, 1, true><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(P, h->X, h->U, x0, yref, yref_mode,
                                                                                                   h->ws, u0, status, iters, i0, nb, skip);
         else if (nb >= h->qp8_batch) {
             // one wave of resident warps; their groups draw the chunk's instances from the work counter
             const int want = (nb + kGPW - 1) / kGPW;
             const int grid = want < h->qp8_resident ? want : h->qp8_resident;
             CK(h, cudaMemsetAsync(h->qp8_next, 0, sizeof(unsigned), s));
-            qp8_kernel<NX, NU><<<grid, 32, 0, s>>>(h->P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb, h->qp8_next, skip);
+            qp8_kernel<NX, NU><<<grid, 32, 0, s>>>(P, h->X, h->U, x0, yref, yref_mode, h->ws, u0, status, iters, i0, nb, h->qp8_next);
         }
         else if (nb >= h->throughput_batch)
-            qp_kernel<NX, NU, kWPB, 1, MPCB_TP_MINB, false><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+            qp_kernel<NX, NU, kWPB, 1, MPCB_TP_MINB, false><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(P, h->X, h->U, x0, yref, yref_mode,
                                                                                                     h->ws, u0, status, iters, i0, nb, skip);
         else
-            qp_kernel<NX, NU, kWPB, 2, 1, false><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(h->P, h->X, h->U, x0, yref, yref_mode,
+            qp_kernel<NX, NU, kWPB, 2, 1, false><<<(nb + kWPB - 1) / kWPB, 32 * kWPB, smem, s>>>(P, h->X, h->U, x0, yref, yref_mode,
                                                                                                    h->ws, u0, status, iters, i0, nb, skip);
         if (prof) cudaEventRecord(h->ev[2], s);
         g_launches += 1;
         if (sqp) {
             const size_t per = (size_t)(h->N + 1) * L::NZ;
-            sqp_book_kernel<NX, NU><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(h->P, h->ws, *sqp, status, iters, i0, nb);
+            sqp_book_kernel<NX, NU><<<(unsigned)((per * nb + 255) / 256), 256, 0, s>>>(P, h->ws, *sqp, status, iters, i0, nb);
             g_launches += 1;
         }
     }

@@ -333,7 +333,6 @@ struct Qp8Batch {
     int32_t *status, *iters;
     int inst0, B;
     unsigned *next;            // work counter of the chunk (zero at launch)
-    const int32_t *skip;       // optional, whole batch: instances flagged non-zero are not solved (SQP: already converged)
 };
 
 // Explicit max-norms of the dynamics and bound-slack residuals of a group's QP iterate (see explicit_residuals in
@@ -528,11 +527,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
         const bool want = !has && !drained;
         if (warp_or(want ? 1 : 0)) {
             int idx = 0;
-            if (want && s == 0) {
-                idx = (int)queue_take(job.next);
-                if (job.skip)
-                    while (idx < job.B && job.skip[job.inst0 + idx]) idx = (int)queue_take(job.next);
-            }
+            if (want && s == 0) idx = (int)queue_take(job.next);
             idx = warp_shfl(idx, lane & ~(kLPI - 1));
             const bool fresh = want && idx < job.B;
             if (want && !fresh) drained = true;

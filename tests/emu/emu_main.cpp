@@ -125,7 +125,7 @@ static void rti_four(const Params &P, int nb, double *X, double *U, const double
     unsigned next = 0;
     Qp8Batch job;
     job.X = X; job.U = U; job.x0 = x0; job.yref = yref; job.yref_stride = NX + NU; job.yps = 0;
-    job.ws = ws.data(); job.u0 = nullptr; job.status = status; job.iters = iters; job.inst0 = 0; job.B = nb; job.next = &next; job.skip = nullptr;
+    job.ws = ws.data(); job.u0 = nullptr; job.status = status; job.iters = iters; job.inst0 = 0; job.B = nb; job.next = &next;
     emu::run_warp([&]() { qp8_solve_queue<NX, NU>(P, sm, job); });
 }
 extern "C" void emu_rti_solve4(const Params *P, int nb, double *X, double *U, const double *x0, const double *yref, const double *p,

@@ -313,12 +313,12 @@ def test_sqp_to_convergence_c_oracle_matches_numpy_oracle():
     P = bo.canonical_problem(N)
     x0, yref = sc.random_setpoints(3, seed=11)
     trim = sc.hover_trim()
-    c = co.BatchRTI(P, 3, nthreads=1)
+    c = co.BatchRTI(P, 3, nthreads=1, strict=True, max_iter=60)  # the product solves the QPs of this mode with the refined rule set
     c.reset(x0, trim)
     u0, Xc, Uc, st, n_qp, qp_it, res = c.sqp_solve(x0, yref, max_iter=100, tol=1e-6)
     assert (st == 0).all() and (n_qp >= 2).all() and (n_qp < 30).all() and (res <= 1e-6).all(), (st, n_qp, res)
     for i in range(3):
-        o = bo.RTIOracle(P)
+        o = bo.RTIOracle(P, strict=True, max_iter=60)
         o.reset(x0[i], trim)
         _, Xo, Uo, sto, n_o, it_o, res_o = o.sqp_solve(x0[i], yref[i], max_iter=100, tol=1e-6)
         assert sto == 0 and n_o == n_qp[i] and it_o == qp_it[i], (i, sto, n_o, n_qp[i], it_o, qp_it[i])
@@ -331,7 +331,7 @@ def test_sqp_to_convergence_c_oracle_matches_numpy_oracle():
     # one SQP iteration from the same start is the RTI step
     c.reset(x0, trim)
     _, X1, U1, _, _, _, _ = c.sqp_solve(x0, yref, max_iter=1, tol=0.0)
-    r = co.BatchRTI(P, 3, nthreads=1)
+    r = co.BatchRTI(P, 3, nthreads=1, strict=True, max_iter=60)
     r.reset(x0, trim)
     _, Xr, Ur, _ = r.solve(x0, yref)
     assert np.array_equal(X1, Xr) and np.array_equal(U1, Ur)
