@@ -17,7 +17,7 @@ class OrcProblem(C.Structure):
                 ("lbx", C.c_double * 17), ("ubx", C.c_double * 17), ("lbu", C.c_double * 6), ("ubu", C.c_double * 6),
                 ("ipm_max_iter", C.c_int), ("rg_mode", C.c_int), ("ric_alg", C.c_int), ("ipm_mu0", C.c_double), ("ipm_thr0", C.c_double),
                 ("tol_stat", C.c_double), ("tol_eq", C.c_double), ("tol_ineq", C.c_double), ("tol_comp", C.c_double), ("alpha_min", C.c_double),
-                ("strict", C.c_int), ("itref", C.c_int)]
+                ("strict", C.c_int), ("itref", C.c_int), ("mixed_mu", C.c_double)]
 
 
 _lib = None
@@ -40,7 +40,7 @@ def _dp(a):
 
 
 def make_problem(P: BlasterProblem, max_iter=None, mu0=1e2, thr0=-0.5, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8,
-                 tol_comp=1e-8, ric_alg=1, rg_mode=2, alpha_min=1e-8, strict=False, itref=None) -> OrcProblem:
+                 tol_comp=1e-8, ric_alg=1, rg_mode=2, alpha_min=1e-8, strict=False, itref=None, mixed_mu=0.0) -> OrcProblem:
     """``strict``: the reference stack's semantics (mpcb_config.strict_reference) -- explicit residual norms in the stopping
     test, no divergence exit, last iterate applied on max-iter, iteration cap 500 (blastermodel.py:279) unless given, one
     step of iterative refinement on the corrector solve (what makes the explicit stationarity norm reach 1e-6)."""
@@ -48,6 +48,7 @@ def make_problem(P: BlasterProblem, max_iter=None, mu0=1e2, thr0=-0.5, tol_stat=
     if max_iter is None:
         max_iter = 500 if strict else 60
     o.strict = int(bool(strict))
+    o.mixed_mu = float(mixed_mu)
     o.itref = int((1 if strict else 0) if itref is None else itref)  # strict: one refinement step on the corrector solve, as the kernel's STRICT instantiation
     o.variant, o.N, o.dt, o.mass = P.variant, P.N, P.dt, P.mass
     o.J[:] = P.J.reshape(-1)

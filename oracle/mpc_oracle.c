@@ -39,6 +39,8 @@ typedef struct {
     int strict; /* reference semantics (mpcb_config.strict_reference): explicit residual norms in the stopping test (rg_mode 1
                    is then implied), no early exit on diverging multipliers, last iterate applied on max-iter */
     int itref;  /* iterative-refinement steps on the corrector solve (experiment / strict mode; 0 = none) */
+    double mixed_mu; /* experiment (tools/mixed_precision_viability.py): > 0 = the stage factorisation (W = [B A]'L, Gram matrix,
+                        Cholesky) is done in FP32 while mixed_mu < mu <= mu0; FP64 Householder LQ otherwise */
 } orc_problem;
 
 #define GRAV 9.81 /* blastermodel.py:93 */

@@ -121,8 +121,9 @@ static void SFX(plant_step)(const orc_problem *P, const double *x, const double 
 /* ---- A6: backward Riccati factorisation in square-root form (HPIPM's default
  *      algorithm class):  M_k = diag(Hd_k) + BAt_k P_{k+1} BAt_k',  P_{k+1} = Lxx Lxx',
  *      L_k = chol(M_k) = [Luu 0; Lxu Lxx].  Returns 0, or 1 when a pivot is not positive. */
-static int SFX(ric_factor)(const orc_problem *P, SFX(ws_t) * w, int N)
+static int SFX(ric_factor)(const orc_problem *P, SFX(ws_t) * w, int N, double mu)
 {
+    const int f32 = P->mixed_mu > 0.0 && mu > P->mixed_mu && mu <= P->ipm_mu0;
     double *LN = w->L + (size_t)N * NZ * NZ;
     for (int i = 0; i < NZ * NZ; i++) LN[i] = 0.0;
     for (int i = NU; i < NZ; i++) {
@@ -141,7 +142,65 @@ static int SFX(ric_factor)(const orc_problem *P, SFX(ws_t) * w, int N)
                 for (int j = c; j < NX; j++) acc += BAt[i * NX + j] * Ln[(NU + j) * NZ + NU + c];
                 W[i][c] = acc;
             }
-        if (P->ric_alg == 0) {
+        if (f32 && P->ric_alg == 1 && getenv("ORC_MIXED_LQ")) {
+            /* mixed-precision experiment, second form: the Householder LQ itself in FP32 (no pivot can go negative) */
+            float Wf[NZ][NX];
+            for (int i = 0; i < NZ; i++)
+                for (int c = 0; c < NX; c++) {
+                    float acc = 0.0f;
+                    for (int j = c; j < NX; j++) acc += (float)BAt[i * NX + j] * (float)Ln[(NU + j) * NZ + NU + c];
+                    Wf[i][c] = acc;
+                }
+            for (int i = 0; i < NZ * NZ; i++) L[i] = 0.0;
+            for (int j = 0; j < NZ; j++) {
+                const float hd = (float)w->Hd[(size_t)k * NZ + j];
+                if (!(hd > 0.0f)) return 1;
+                const float d = sqrtf(hd);
+                float s2 = hd;
+                for (int c = 0; c < NX; c++) s2 += Wf[j][c] * Wf[j][c];
+                const float sig = sqrtf(s2);
+                const float v0 = d + sig;
+                const float beta = 1.0f / (sig * v0);
+                L[j * NZ + j] = (double)sig;
+                for (int i = j + 1; i < NZ; i++) {
+                    float dot = 0.0f;
+                    for (int c = 0; c < NX; c++) dot += Wf[j][c] * Wf[i][c];
+                    const float f = beta * dot;
+                    L[i * NZ + j] = (double)(f * v0);
+                    for (int c = 0; c < NX; c++) Wf[i][c] -= f * Wf[j][c];
+                }
+            }
+        } else if (f32) {
+            /* mixed-precision experiment: the same normal-equations factorisation with every operand and operation in FP32 */
+            float Wf[NZ][NX], Lf[NZ][NZ];
+            for (int i = 0; i < NZ; i++)
+                for (int c = 0; c < NX; c++) {
+                    float acc = 0.0f;
+                    for (int j = c; j < NX; j++) acc += (float)BAt[i * NX + j] * (float)Ln[(NU + j) * NZ + NU + c];
+                    Wf[i][c] = acc;
+                }
+            for (int i = 0; i < NZ; i++)
+                for (int j = 0; j <= i; j++) {
+                    float acc = (i == j) ? (float)w->Hd[(size_t)k * NZ + i] : 0.0f;
+                    for (int c = 0; c < NX; c++) acc += Wf[i][c] * Wf[j][c];
+                    Lf[i][j] = acc;
+                }
+            for (int j = 0; j < NZ; j++) {
+                float d = Lf[j][j];
+                for (int c = 0; c < j; c++) d -= Lf[j][c] * Lf[j][c];
+                if (!(d > 0.0f)) return 1;
+                d = sqrtf(d);
+                Lf[j][j] = d;
+                const float inv = 1.0f / d;
+                for (int i = j + 1; i < NZ; i++) {
+                    float sacc = Lf[i][j];
+                    for (int c = 0; c < j; c++) sacc -= Lf[i][c] * Lf[j][c];
+                    Lf[i][j] = sacc * inv;
+                }
+            }
+            for (int i = 0; i < NZ; i++)
+                for (int j = 0; j < NZ; j++) L[i * NZ + j] = (j <= i) ? (double)Lf[i][j] : 0.0;
+        } else if (P->ric_alg == 0) {
             /* classical normal-equations form: M = Hd + W W', Cholesky (kept for experiments) */
             for (int i = 0; i < NZ; i++)
                 for (int j = 0; j <= i; j++) {
@@ -441,7 +500,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
             for (size_t i = 0; i < n; i++) { double gm = w->Hd[i] - w->H0[i]; if (gm > gmax) gmax = gm; if ((int)(i % NZ) >= NU && gm > gxmax) gxmax = gm; }
             fprintf(stderr, "   barrier max %.3e  (states %.3e)\n", gmax, gxmax);
         }
-        if (SFX(ric_factor)(P, w, N)) { status = 4; break; }
+        if (SFX(ric_factor)(P, w, N, mu)) { status = 4; break; }
         double alpha = 1.0;
         if (nb) {
             /* predictor */
