@@ -37,6 +37,11 @@ namespace mpcb {
 #ifndef MPCB_GRAM_MU
 #define MPCB_GRAM_MU 1e-5
 #endif
+// W = [B A]' Lxx and the Gram matrix W W' of the latency variant on the FP64 tensor cores (mma.sync m8n8k4, DMMA):
+// -DMPCB_DMMA=0 restores the CUDA-core products (tools/ab.py).
+#ifndef MPCB_DMMA
+#define MPCB_DMMA 1
+#endif
 constexpr double kMuDiverge = 1e2;  // infeasibility test: mu > kMuDiverge * mu0 (the CPU checkers apply the same test; no feasible instance of the test scenarios exceeds 3 * mu0)
 
 // Per-warp shared memory: two stage-record images (same offsets as the global record) plus
@@ -623,6 +628,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     q += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
                 }
             }
+            constexpr bool kDmma = (NSLOT == 2) && (MPCB_DMMA != 0);
+            if (kDmma && lane < NZ) sm.hd[lane] = Hd;  // read back per tile after the Gram product (a warp_sync lies between)
             // r_k = b_k + [B A] z_k - dx-part of z_{k+1}
             if (lane < NX) {
                 T a0 = s[L::O_B + lane] - sm.cZx[lane], a1 = T(0), a2 = T(0), a3 = T(0);
@@ -645,14 +652,59 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             apply_P<NX, NU, T, NSLOT>(sm);
             // carry this stage's pi and dx-part of z to stage k-1 (cPi / cZx were consumed above)
             if (lane < NX) { sm.cPi[lane] = s[L::O_PI + lane]; sm.cZx[lane] = s[L::O_Z + NU + lane]; }
-            // W = [B A]' Lxx_{k+1}   (row `lane`)
-            T w[NX];
-            MPCB_UNROLL
-            for (int c = 0; c < NX; c++) {
-                T a = T(0);
+            // affine backward vector before the substitution: l = q + [B A]' t2 (the last use of this lane's row of [B A]')
+            T lin;
+            {
+                T l0 = q, l1 = T(0);
                 MPCB_UNROLL
-                for (int j = c; j < NX; j++) a += brow[j] * sm.Lxx[j * NX + c];
-                w[c] = a;
+                for (int c = 0; c + 1 < NX; c += 2) { l0 += brow[c] * sm.sT2[c]; l1 += brow[c + 1] * sm.sT2[c + 1]; }
+                if (NX & 1) l0 += brow[NX - 1] * sm.sT2[NX - 1];
+                lin = l0 + l1;
+            }
+            // W = [B A]' Lxx_{k+1}
+            T w[NX];  // row `lane` of W (CUDA-core product, or read back from the tiles for the Householder loop)
+            // Tensor-core form: W as NI x NJ tiles of 8 x 8, accumulated over NS k-steps of 4 rows of Lxx (lower triangular:
+            // tiles above the diagonal band are skipped).  Lane 4 g + q supplies A = [B A]'[8 I + g][4 s + q] and
+            // B = Lxx[4 s + q][8 J + g] straight from the record image / the factor in shared memory and ends up with
+            // W[8 I + g][8 J + 2 q + h], h = 0, 1.  27 DMMAs + 24 loads instead of 153 DFMAs + 153 broadcast loads (BLASTER17).
+            constexpr int NI = (NZ + 7) / 8, NJ = (NX + 7) / 8, NS = (NX + 3) / 4;
+            const int tg = lane >> 2, tq = lane & 3;
+            T wt[NI][NJ][2];
+            if constexpr (kDmma) {
+                static_for<0, NI>([&](auto I_) {
+                    static_for<0, NJ>([&](auto J_) { wt[decltype(I_)::value][decltype(J_)::value][0] = T(0); wt[decltype(I_)::value][decltype(J_)::value][1] = T(0); });
+                });
+                static_for<0, NS>([&](auto S_) {
+                    constexpr int st = decltype(S_)::value;
+                    const int kk = 4 * st + tq;       // row of Lxx = column of [B A]' of this lane's fragments
+                    const bool kin = kk < NX;
+                    T af[NI];
+                    static_for<0, NI>([&](auto I_) {
+                        constexpr int I = decltype(I_)::value;
+                        const int row = 8 * I + tg;
+                        const bool in = kin && row < NZ;
+                        const T v = s[L::O_BAT + (in ? row * L::LDB + kk : 0)];
+                        af[I] = in ? v : T(0);
+                    });
+                    static_for<0, NJ>([&](auto J_) {
+                        constexpr int J = decltype(J_)::value;
+                        if constexpr (8 * J <= 4 * st + 3) {  // some row of this k-step reaches the tile's columns (Lxx[j][c] = 0 for c > j)
+                            const int col = 8 * J + tg;
+                            const bool in = kin && col < NX;
+                            const T v = sm.Lxx[in ? kk * NX + col : 0];
+                            const T bf = in ? v : T(0);
+                            static_for<0, NI>([&](auto I_) { constexpr int I = decltype(I_)::value; warp_dmma(wt[I][J][0], wt[I][J][1], af[I], bf); });
+                        }
+                    });
+                });
+            } else {
+                MPCB_UNROLL
+                for (int c = 0; c < NX; c++) {
+                    T a = T(0);
+                    MPCB_UNROLL
+                    for (int j = c; j < NX; j++) a += brow[j] * sm.Lxx[j * NX + c];
+                    w[c] = a;
+                }
             }
             T Lu[NU], invd[NU];
             constexpr bool kGramFactor = (NSLOT == 2) && (MPCB_GRAM_MU < 1e29);
@@ -669,17 +721,68 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 constexpr int LDW = (NX + 1) & ~1;  // rows of the W image stay 16-byte aligned
                 static_assert(NZ * LDW <= L::STAGE - L::O_C1, "the W image must fit the part of the record image this sweep does not fetch");
                 static_assert(2 * L::NZP <= L::NZ * L::NUP, "column buffer must fit sm.Lcol");
-                if (lane >= NZ) {
+                if (!kDmma && lane >= NZ) {
                     MPCB_UNROLL
                     for (int c = 0; c < NX; c++) w[c] = T(0);
                 }
                 T *Wsh = sm.slot[half] + L::O_C1;
-                sp_row_store<0, NX>(sptr_of(Wsh + (lane < NZ ? lane : 0) * LDW), w, lane < NZ);
-                warp_sync();
-                const sptr w0 = sptr_of(Wsh);
                 T m[NZ + 1];
                 MPCB_UNROLL
                 for (int c = 0; c <= NZ; c++) m[c] = T(0);
+                if constexpr (kDmma) {
+                    // Gram matrix on the tensor cores.  M = W W' contracts over the columns of W, and ANY assignment of columns
+                    // to k-indices is a valid contraction as long as A and B use the same one: lane (g, q) feeds the
+                    // entries of W it already holds -- W[8 I + g][8 Jc + 2 q + h] as A, W[8 J + g][8 Jc + 2 q + h] as B -- so
+                    // the k-steps run over (Jc, h) with no data movement at all: NI (NI + 1) / 2 x 2 NJ DMMAs (36, BLASTER17).
+                    T mt[NI][NI][2];
+                    static_for<0, NI>([&](auto I_) {
+                        static_for<0, NI>([&](auto J_) { mt[decltype(I_)::value][decltype(J_)::value][0] = T(0); mt[decltype(I_)::value][decltype(J_)::value][1] = T(0); });
+                    });
+                    static_for<0, NJ>([&](auto C_) {
+                        constexpr int Jc = decltype(C_)::value;
+                        static_for<0, 2>([&](auto H_) {
+                            constexpr int h = decltype(H_)::value;
+                            static_for<0, NI>([&](auto I_) {
+                                constexpr int I = decltype(I_)::value;
+                                static_for<0, I + 1>([&](auto J_) {
+                                    constexpr int J = decltype(J_)::value;
+                                    warp_dmma(mt[I][J][0], mt[I][J][1], wt[I][Jc][h], wt[J][Jc][h]);
+                                });
+                            });
+                        });
+                    });
+                    // tiles -> rows: block I (rows 8 I .. 8 I + 7) is stored with 8 (I + 1) columns at an even, padded stride
+                    // (bank-conflict-free 128-bit row reads); the diagonal gets Hd on its way; lane r then reads row r.
+                    // Entries right of a block's width belong to the unused upper triangle: whatever is read there never
+                    // reaches a stored value (column j of L only takes m[j] of the lanes below the diagonal).
+                    auto moff = [](int I) { return 8 * (4 * I * (I + 1) + 2 * I); };      // sum_{i<I} 8 (8 (i + 1) + 2)
+                    auto mstride = [](int I) { return 8 * (I + 1) + 2; };
+                    static_assert(8 * (4 * (NI - 1) * NI + 2 * (NI - 1)) + ((NZ - 1) % 8) * (8 * NI + 2) + L::NZP <= L::STAGE - L::O_C1,
+                                  "the Gram image (and a full-width read of its last row) must fit the free tail of the record image");
+                    static_for<0, NI>([&](auto I_) {
+                        constexpr int I = decltype(I_)::value;
+                        const bool rin = 8 * I + tg < NZ;
+                        // Hd of row 8 I + g sits on the diagonal tile in lane q = g / 2, element g % 2
+                        const T hdv = sm.hd[rin ? 8 * I + tg : 0];
+                        if (rin && (tg >> 1) == tq) { if (tg & 1) mt[I][I][1] += hdv; else mt[I][I][0] += hdv; }
+                        static_for<0, I + 1>([&](auto J_) {
+                            constexpr int J = decltype(J_)::value;
+                            sp_st2<0>(sptr_of(Wsh + moff(I) + tg * mstride(I) + 8 * J + 2 * tq), mt[I][J][0], mt[I][J][1], rin);
+                        });
+                    });
+                    warp_sync();
+                    {
+                        const int r = lane < NZ ? lane : 0;
+                        const sptr mrow = sptr_of(Wsh + moff(r >> 3) + (r & 7) * mstride(r >> 3));
+                        static_for<0, NZ, 2>([&](auto Cc) {
+                            constexpr int c = decltype(Cc)::value;
+                            sp_ld2<c>(mrow, m[c], m[c + 1]);
+                        });
+                    }
+                } else {
+                sp_row_store<0, NX>(sptr_of(Wsh + (lane < NZ ? lane : 0) * LDW), w, lane < NZ);
+                warp_sync();
+                const sptr w0 = sptr_of(Wsh);
                 auto gram = [&](auto C) {
                     constexpr int c = decltype(C)::value;
                     T v[NX];
@@ -693,6 +796,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 };
                 static_for<0, NU>(gram);
                 if (k > 0) static_for<NU, NZ>(gram);
+                }
                 const sptr cb0 = sptr_of(sm.Lcol);
                 const sptr cbl = sptr_add(cb0, lane < NZ ? lane : 0);
                 T sig = T(1);
@@ -724,6 +828,22 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             } else {
             const T dsq = sqrt(Hd);
             if (lane < NZ) { sm.hd[lane] = Hd; sm.ds[lane] = dsq; }  // visible after the first pivot's warp_sync
+            if constexpr (kDmma) {
+                // the Householder loop works on row `lane` of W in registers: tiles -> W image -> rows
+                constexpr int LDW = (NX + 1) & ~1;
+                static_assert(NZ * LDW <= L::STAGE - L::O_C1, "the W image must fit the part of the record image this sweep does not fetch");
+                T *Wsh = sm.slot[half] + L::O_C1;
+                static_for<0, NI>([&](auto I_) {
+                    constexpr int I = decltype(I_)::value;
+                    static_for<0, NJ>([&](auto J_) {
+                        constexpr int J = decltype(J_)::value;
+                        const int row = 8 * I + tg;
+                        sp_st2<0>(sptr_of(Wsh + (row < NZ ? row : 0) * LDW + 8 * J + 2 * tq), wt[I][J][0], wt[I][J][1], row < NZ && 8 * J + 2 * tq < LDW);
+                    });
+                });
+                warp_sync();
+                sp_row_load<0, NX>(sptr_of(Wsh + (lane < NZ ? lane : 0) * LDW), w);
+            }
             // Householder LQ of [diag(dsq) | W], one pivot row per step:
             //   sigma^2 = Hd_j + |w_j|^2,  L_ij = (w_i . w_j)/sigma,
             //   w_i -= L_ij * kappa * w_j,  kappa = 1/(sigma + dsq_j) = (sigma - dsq_j)/|w_j|^2
@@ -796,12 +916,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             MPCB_UNROLL
             for (int c = 0; c < NU; c++) { Lu[c] = sm.Lcol[(lane < NZ ? lane : 0) * L::NUP + c]; invd[c] = sm.Linv[c]; }
             }
-            // affine backward vectors: l = q + [B A]' t2
-            T l0 = q, l1 = T(0);
-            MPCB_UNROLL
-            for (int c = 0; c + 1 < NX; c += 2) { l0 += brow[c] * sm.sT2[c]; l1 += brow[c + 1] * sm.sT2[c + 1]; }
-            if (NX & 1) l0 += brow[NX - 1] * sm.sT2[NX - 1];
-            const T l = fwd_subst<NU, T>(l0 + l1, Lu, invd, NZ);
+            const T l = fwd_subst<NU, T>(lin, Lu, invd, NZ);
             if (lane < NU) wk[L::O_LVEC + lane] = l;
             else if (lane < NZ) { wk[L::O_PV + lane - NU] = l; sm.cPv[lane - NU] = l; }
             if (lane < NZ) {

@@ -199,8 +199,8 @@ def test_hybrid_factorisation_agrees_with_householder_only_build(tmp_path):
     for k, tag in ((k, tag) for k in res["lq"].files for tag in ("hybrid",)):
         a, b = res[tag][k], res["lq"][k]
         assert a[0] == b[0] == 0 and a[1] == b[1], (k, tag)    # status, IPM iterations
-        # measured: hybrid 2e-12; Gram on every iteration 1e-9 on these cases and 8e-6 on cold random set-points
-        assert np.abs(a[2:] - b[2:]).max() < 5e-11, (k, np.abs(a[2:] - b[2:]).max())
+        # measured: hybrid 2e-12 (CUDA-core products), 6e-11 (tensor-core products: another summation order); Gram on every iteration 1e-9 on these cases and 8e-6 on cold random set-points
+        assert np.abs(a[2:] - b[2:]).max() < 5e-10, (k, np.abs(a[2:] - b[2:]).max())
 
 
 def test_emulated_kernel_infeasible_instance_keeps_the_checkers_status():
