@@ -21,10 +21,6 @@
 //   Per IPM iteration the stage matrices are read four times and L is written once.
 #pragma once
 #include "mpcb_common.cuh"
-#ifdef MPCB_HOST_EMU
-#include <cstdio>
-#include <cstdlib>
-#endif
 
 namespace mpcb {
 
@@ -628,6 +624,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     q += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
                 }
             }
+            // latency variant only: measured on the single-buffer throughput variant (168-register cap, Householder LQ on every
+            // iteration, so only the W product moves) it is 0.4 .. 1 % slower (profiles/r02_ab_dmma_tp.txt)
             constexpr bool kDmma = (NSLOT == 2) && (MPCB_DMMA != 0);
             if (kDmma && lane < NZ) sm.hd[lane] = Hd;  // read back per tile after the Gram product (a warp_sync lies between)
             // r_k = b_k + [B A] z_k - dx-part of z_{k+1}
@@ -868,15 +866,10 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 const sptr vr = sptr_add(vr0, (j & 1) * L::NXP);
                 const bool piv = (lane == j);
                 T v[NX];
-#ifndef MPCB_PIVOT_VIA_SHFL  // shared-memory broadcast (default): same latency as 34 shuffles, less MIO pressure at high occupancy
+                // shared-memory broadcast of the pivot row: same latency as 34 shuffles, less MIO pressure (measured in round 1)
                 sp_row_store<0, NX>(vr, w, piv);
                 warp_sync();
                 sp_row_load<0, NX>(vr, v);
-#else
-                (void)vr;
-                MPCB_UNROLL
-                for (int c = 0; c < NX; c++) v[c] = warp_shfl(w[c], j);
-#endif
                 T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);
                 MPCB_UNROLL
                 for (int c = 0; c + 3 < NX; c += 4) {
@@ -938,9 +931,6 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
         if (STRICT) {
             // reference semantics: test the residuals S1 has just evaluated on this iterate (before using the factorisation)
             xg = warp_max(xg); xb = warp_max(xb); xd = warp_max(xd);
-#ifdef MPCB_HOST_EMU
-            if (getenv("MPCB_EMU_DEBUG") && lane == 0) fprintf(stderr, "emu it %d res_g %.3e res_b %.3e res_d %.3e comp %.3e mu %.3e\n", it, (double)xg, (double)xb, (double)xd, (double)comp, (double)mu);
-#endif
             if (!(xg == xg) || !(xb == xb)) { status = ST_NAN; break; }
             if (xg <= (T)P.tol_stat && xb <= (T)P.tol_eq && xd <= (T)P.tol_ineq && comp <= (T)P.tol_comp) { status = ST_OK; break; }
         }
@@ -1067,9 +1057,6 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     rho = Hd * dz + r + dsum;
                 }
                 if (lane < NZ) { wk[L::O_C1 + lane] = rho; wk[L::O_C2 + lane] = T(0); }
-#ifdef MPCB_HOST_EMU
-                if (getenv("MPCB_EMU_DEBUG")) { const T m_ = warp_max(fabs(rho)); if (lane == 0 && m_ > 1e-9) fprintf(stderr, "   emu rho stage %d: %.3e\n", k, (double)m_); }
-#endif
             }
             pipe_fence();
             warp_sync();

@@ -750,16 +750,6 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                     MPCB_UNROLL
                     for (int c = 0; c < NX; c++) v[c] = vr[c];
                     double djj;
-#ifdef MPCB_Q8_SHFL_DJJ
-                    {
-                        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-                        MPCB_UNROLL
-                        for (int c = 0; c + 3 < NX; c += 4) { d0 += v[c] * w[tj][c]; d1 += v[c + 1] * w[tj][c + 1]; d2 += v[c + 2] * w[tj][c + 2]; d3 += v[c + 3] * w[tj][c + 3]; }
-                        MPCB_UNROLL
-                        for (int c = NX & ~3; c < NX; c++) d0 += v[c] * w[tj][c];
-                        djj = grp_bcast((d0 + d1) + (d2 + d3), jj);
-                    }
-#else
                     {
                         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
                         MPCB_UNROLL
@@ -768,7 +758,6 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                         for (int c = NX & ~3; c < NX; c++) d0 += v[c] * v[c];
                         djj = (d0 + d1) + (d2 + d3);
                     }
-#endif
                     const double s2v = hdj + djj;
                     const double rs = fast_rsqrt(s2v);
                     const double idjj = fast_rcp(djj);
@@ -913,10 +902,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
         }
         // ================= F4b: take the step (KU stages per trip: their loads are all in flight together)
         {
-#ifndef MPCB_Q8_KU
-#define MPCB_Q8_KU 1
-#endif
-            constexpr int KU = MPCB_Q8_KU;
+            constexpr int KU = 1;  // stages per trip (more in flight together was measured slower: register pressure)
             double cmax = 0.0, msum = 0.0;
             for (int k0 = 0; k0 <= N; k0 += KU) {
                 double z[KU][NT], dz[KU][NT], tl[KU][NT], tu[KU][NT], ll[KU][NT], lu[KU][NT], lb[KU][NT], ub[KU][NT], dza[KU][NT];

@@ -5,17 +5,17 @@
 # kernels (16,384 instances: throughput variant of qp_kernel, persistent qp8_kernel on both models).
 # Raw outputs go to gpurun_out/; tools/summarize_profiles.py turns them into profiles/<tag>_*.md here.
 set -e
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 6 --warmup 2 --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1
+    python bench.py --steps 6 --warmup 3 --no-cpu --no-large --no-quad12 > gpurun_out/${TAG}_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 8 -c 2 -f \
-    -o gpurun_out/${TAG}_full python bench.py --steps 6 --warmup 2 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
+    -o gpurun_out/${TAG}_full python bench.py --steps 6 --warmup 3 --no-cpu --no-large --no-quad12 > gpurun_out/${TAG}_ncu_full.log 2>&1
 [ "$2" = bench ] && { ls -la gpurun_out; exit 0; }   # `sh tools/profile_round.sh <tag> bench`: only the bench step's kernels
 # large batches: the one-instance throughput variant (forced: chunks of this size default to qp8_kernel), then qp8_kernel on both models
-MPCB_QP8_BATCH=1000000000 ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 2 -c 2 -f \
-    -o gpurun_out/${TAG}_qp1_blaster17_16k python tools/sweep.py --points "16384,20,17,rand" > gpurun_out/${TAG}_ncu_16k_17.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 2 -c 2 -f \
+    -o gpurun_out/${TAG}_qp1_blaster17_16k python tools/sweep.py --points "16384,20,17,rand" --qp8-batch 1000000000 > gpurun_out/${TAG}_ncu_16k_17.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'qp8_kernel' -s 1 -c 1 -f \
     -o gpurun_out/${TAG}_qp8_blaster17_16k python tools/sweep.py --points "16384,20,17,rand" > gpurun_out/${TAG}_ncu_16k_17_qp8.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp8_kernel' -s 2 -c 2 -f \

@@ -14,9 +14,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mpc_blaster_b200 import BlasterMPC, scenarios as sc  # noqa: E402
 
 
-def run(B, N, variant, scen, steps=5, warmup=2, ws_batch=0):
+def run(B, N, variant, scen, steps=5, warmup=2, ws_batch=0, **kw):
     nx, nu = {17: (17, 6), 12: (12, 4), 13: (13, 4)}[variant]
-    mpc = BlasterMPC.canonical(N=N, batch=B, variant=variant, ws_batch=ws_batch)
+    mpc = BlasterMPC.canonical(N=N, batch=B, variant=variant, ws_batch=ws_batch, **kw)
     if scen == "track":
         x0, yref = sc.lemniscate_tracking(B, N, nx=nx, nu=nu)
     else:
@@ -51,7 +51,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--points", default="1024,20,17,rand;4096,20,17,rand;16384,20,17,rand;65536,20,17,rand;1024,20,12,rand;16384,20,12,rand;"
                                         "65536,40,17,track;16384,80,17,rand")
+    ap.add_argument("--qp8-batch", type=int, default=0, help="mpcb_config.qp8_batch (0 = default; huge = never use the four-instances-per-warp kernel)")
+    ap.add_argument("--throughput-batch", type=int, default=0, help="mpcb_config.throughput_batch (0 = default)")
+    ap.add_argument("--strict", action="store_true", help="mpcb_config.strict_reference")
     a = ap.parse_args()
     for pt in a.points.split(";"):
         B, N, v, scen = pt.split(",")
-        run(int(B), int(N), int(v), scen)
+        run(int(B), int(N), int(v), scen, qp8_batch=a.qp8_batch, throughput_batch=a.throughput_batch, strict_reference=a.strict)
