@@ -73,9 +73,9 @@ typedef struct mpcb_config {
     int32_t max_batch;    /* capacity of the persistent iterate (instances) */
     int32_t ws_batch;     /* instances of solver workspace resident at once (0 = auto) */
     int32_t device;       /* CUDA device ordinal, -1 = current */
-    /* Reference-semantics switch.  0 (default): the throughput-oriented stopping rules of DESIGN.md section 2 -- linear
-     * residuals tracked through their exact-arithmetic decay and confirmed explicitly before success is reported,
-     * early exit (status 3) when the multipliers diverge, a failed QP leaves the iterate untouched.  1: what the
+    /* Reference-semantics switch.  0 (default): the throughput-oriented stopping rules of DESIGN.md section 2 -- the
+     * stationarity norm tracked through its exact-arithmetic decay, the dynamics / bound-slack norms measured on every
+     * iterate, early exit (status 3) when the multipliers diverge, a failed QP leaves the iterate untouched.  1: what the
      * reference's stack does -- explicitly evaluated residual norms (stationarity included) in the stopping test, no
      * divergence exit (the interior point runs to ipm_max_iter; the reference sets qp_solver_iter_max = 500,
      * blastermodel.py:279), and the last interior-point iterate is applied when that cap is hit (acados SQP_RTI takes

@@ -335,47 +335,6 @@ struct Qp8Batch {
     unsigned *next;            // work counter of the chunk (zero at launch)
 };
 
-// Explicit max-norms of the dynamics and bound-slack residuals of a group's QP iterate (see explicit_residuals in
-// mpcb_qp.cuh), for the groups with `act` set; warp-uniform control flow.
-template <int NX, int NU>
-MPCB_DEV void qp8_explicit_residuals(const double *__restrict__ ws, int N, bool act, double &res_b, double &res_d)
-{
-    using L = Layout<NX, NU>;
-    constexpr int NZ = L::NZ, NT = (NZ + kLPI - 1) / kLPI, NXT = (NX + kLPI - 1) / kLPI;
-    const int s = lane_id() & (kLPI - 1);
-    double eb = 0.0, ed = 0.0;
-    MPCB_NOUNROLL
-    for (int k = 0; k <= N; k++) {
-        const double *wk = ws + (size_t)k * L::STAGE;
-        MPCB_UNROLL
-        for (int t = 0; t < NT; t++) {
-            const int row = s + kLPI * t;
-            if (act && row < NZ && var_kind<NX, NU>(k, row, N).hasb) {
-                const double z = wk[L::O_Z + row];
-                ed = fmax(ed, fmax(fabs(z - wk[L::O_LB + row] - wk[L::O_TL + row]), fabs(wk[L::O_UB + row] - z - wk[L::O_TU + row])));
-            }
-        }
-        if (k < N) {
-            MPCB_UNROLL
-            for (int t = 0; t < NXT; t++) {
-                const int i = s + kLPI * t;
-                if (act && i < NX) {
-                    double a0 = wk[L::O_B + i] - wk[L::STAGE + L::O_Z + NU + i], a1 = 0.0;
-                    MPCB_UNROLL4
-                    for (int j = 0; j + 1 < NZ; j += 2) {
-                        a0 += wk[L::O_BAT + j * L::LDB + i] * wk[L::O_Z + j];
-                        a1 += wk[L::O_BAT + (j + 1) * L::LDB + i] * wk[L::O_Z + j + 1];
-                    }
-                    if (NZ & 1) a0 += wk[L::O_BAT + (NZ - 1) * L::LDB + i] * wk[L::O_Z + NZ - 1];
-                    eb = fmax(eb, fabs(a0 + a1));
-                }
-            }
-        }
-    }
-    res_b = grp_max(eb);
-    res_d = grp_max(ed);
-}
-
 // QP data and cold start of one instance (see F0 in mpcb_qp.cuh), for the groups with `act` set;
 // warp-uniform control flow, so the group reductions at the end are executed by every lane.
 template <int NX, int NU>
@@ -484,21 +443,11 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
     for (;;) {
         // ---- the stopping tests of mpcb_qp.cuh, in the same order (an instance that uses up its iterations is not tested again)
         auto test = [&]() {
-            bool cand = false;
             if (has && !done) {
                 if (git >= P.ipm_max_iter) { status = ST_MAXITER; done = true; }
                 else if (!(est_g == est_g) || !(est_b == est_b) || !(mu == mu)) { status = ST_NAN; done = true; }
                 else if (mu > kMuDiverge * mu0) { status = ST_MINSTEP; done = true; }
-                else if (est_g <= P.tol_stat && est_b <= P.tol_eq && est_d <= P.tol_ineq && comp <= P.tol_comp) cand = true;
-            }
-            // est_b / est_d are extrapolations (res_0 * prod(1 - alpha)): confirm them on the iterate itself before ST_OK
-            if (warp_or(cand ? 1 : 0)) {
-                double xb, xd;
-                qp8_explicit_residuals<NX, NU>(ws, N, cand, xb, xd);
-                if (cand) {
-                    if (xb <= P.tol_eq && xd <= P.tol_ineq) { status = ST_OK; done = true; }
-                    else { est_b = xb; est_d = xd; }
-                }
+                else if (est_g <= P.tol_stat && est_b <= P.tol_eq && est_d <= P.tol_ineq && comp <= P.tol_comp) { status = ST_OK; done = true; }
             }
         };
         test();
@@ -553,6 +502,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
 
         // ================= S1: backward sweep -- residuals, factorisation, affine right-hand side
         double last_sig = 1.0;
+        double xb = 0.0, xd = 0.0;  // explicit dynamics / bound-slack residual norms of this iterate (see mpcb_qp.cuh)
         const bool issue = run && s == 0;
         {
             // terminal stage N: L_N = sqrt(Q_t), p_N = q_N
@@ -613,6 +563,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                     if (hb) {
                         const double itl = fast_rcp(vtl[t]), itu = fast_rcp(vtu[t]);
                         const double rdl = zr[t] - vlb[t] - vtl[t], rdu = vub[t] - zr[t] - vtu[t];
+                        xd = fmax(xd, fmax(fabs(rdl), fabs(rdu)));
                         Hd[t] += vll[t] * itl + vlu[t] * itu;
                         q[t] += (vll[t] + vll[t] * rdl * itl) - (vlu[t] + vlu[t] * rdu * itu);
                     }
@@ -657,7 +608,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                     const int i = s + kLPI * t;
                     if (i < NX) {
                         sm.sRb[i] = a[t];
-                        if (run) wk[L::O_RB + i] = a[t];
+                        if (run) { wk[L::O_RB + i] = a[t]; xb = fmax(xb, fabs(a[t])); }
                     }
                 }
             }
@@ -964,10 +915,12 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
             const double c_ = grp_max(cmax), m_ = grp_sum(msum) / nb;
             if (run2) { comp = c_; mu = m_; }
         }
+        xb = grp_max(xb);
+        xd = grp_max(xd);
         if (run2) {
             est_g *= (1.0 - alpha);
-            est_b *= (1.0 - alpha);
-            est_d *= (1.0 - alpha);
+            est_b = xb * (1.0 - alpha);  // measured on this iterate by S1, then the exact-arithmetic decay of one step
+            est_d = xd * (1.0 - alpha);
             git++;
             if (!(alpha >= P.alpha_min)) {
                 status = (alpha == alpha) ? ST_MINSTEP : ST_NAN;

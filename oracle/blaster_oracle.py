@@ -501,9 +501,9 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
 
     The linear residuals (stationarity, dynamics, bound-slack) enter the stopping test
     through their exact-arithmetic values |r_0| * prod(1 - alpha_j): they are affine in
-    the iterate and everything takes the same step (DESIGN.md "stopping test"); before success
-    is reported the two that can be evaluated exactly (equality, bound slacks) are confirmed on
-    the iterate itself.  ``res`` also carries the explicitly evaluated norms for the tests.
+    the iterate and everything takes the same step (DESIGN.md "stopping test"): stationarity
+    extrapolated from the start, equality and bound-slack residuals as measured on the previous
+    iterate times (1 - alpha).  ``res`` also carries the explicitly evaluated norms for the tests.
 
     ``strict`` (mpcb_config.strict_reference): the reference stack's semantics -- the explicit norms
     (stationarity included) decide the stopping test, there is no early exit on diverging multipliers,
@@ -550,10 +550,8 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
             status = 3
             break
         if res[0] <= tol_stat and res[1] <= tol_eq and res[2] <= tol_ineq and comp <= tol_comp:
-            if strict or (explicit[1] <= tol_eq and explicit[2] <= tol_ineq):
-                status = 0
-                break
-            rb_est, rd_est = explicit[1], explicit[2]  # the extrapolation was too optimistic: go on from the measured values
+            status = 0
+            break
         gam = ll / tl + lu / tu
         K[np.arange(n), np.arange(n)] = H + gam
         lu_piv = _lu_factor(K)
@@ -599,8 +597,8 @@ def ipm_dense(H, g, C, c, lb, ub, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol
         ll = ll + a * dll
         lu = lu + a * dlu
         rg_est *= (1.0 - a)
-        rb_est *= (1.0 - a)
-        rd_est *= (1.0 - a)
+        rb_est = explicit[1] * (1.0 - a)  # measured on this iterate, then the exact-arithmetic decay of one step
+        rd_est = explicit[2] * (1.0 - a)
         if not (a >= alpha_min):
             status = 3 if a == a else 1
             it += 1

@@ -479,9 +479,9 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
         if (nb) mu /= nb;
         if (it == 0) { rg_est = res_g; rb_est = res_b; rd_est = res_d; }
         /* the three linear residuals are affine in the iterate and everything takes the same
-         * step, so each shrinks by exactly (1-alpha); the stopping test uses those values, and
-         * confirms the two that can be evaluated exactly (dynamics, bound slacks) on the iterate
-         * itself before it reports success */
+         * step, so each shrinks by exactly (1-alpha): the stopping test uses the stationarity norm
+         * extrapolated from the start, and for the dynamics / bound-slack residuals the values
+         * MEASURED on the previous iterate times the (1-alpha) of the step since */
         const int extrap = P->rg_mode == 2 && !P->strict;
         const double xb = res_b, xd = res_d;
         if (extrap) { res_g = rg_est; res_b = rb_est; res_d = rd_est; }
@@ -489,10 +489,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
         if (!(res_g == res_g) || !(res_b == res_b) || !(mu == mu)) { status = 1; break; }
         /* diverging multipliers = infeasible QP: stop early, same status as the min-step exit */
         if (!P->strict && mu > 1e2 * mu0) { status = 3; break; }
-        if (res_g <= P->tol_stat && res_b <= P->tol_eq && res_d <= P->tol_ineq && comp <= P->tol_comp) {
-            if (!extrap || (xb <= P->tol_eq && xd <= P->tol_ineq)) { status = 0; break; }
-            rb_est = xb; rd_est = xd;
-        }
+        if (res_g <= P->tol_stat && res_b <= P->tol_eq && res_d <= P->tol_ineq && comp <= P->tol_comp) { status = 0; break; }
         /* factorise with barrier diagonal */
         for (size_t i = 0; i < n; i++) w->Hd[i] = w->H0[i] + w->ll[i] / w->tl[i] + w->lu[i] / w->tu[i];
         if (orc_debug()) {
@@ -541,7 +538,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
          * r_g <- (1-alpha) r_g exactly; evaluating it explicitly needs the multipliers of
          * numerically pinned states, whose absolute accuracy degrades like eps*lam/t. */
         if (P->rg_mode == 0 && !P->strict) for (size_t i = 0; i < n; i++) w->rg[i] *= (1.0 - alpha);
-        rg_est *= (1.0 - alpha); rb_est *= (1.0 - alpha); rd_est *= (1.0 - alpha);
+        rg_est *= (1.0 - alpha); rb_est = xb * (1.0 - alpha); rd_est = xd * (1.0 - alpha);
         if (!(alpha >= P->alpha_min)) { status = (alpha == alpha) ? 3 : 1; it++; break; } /* [upstream D9] 3 = min step */
     }
     *iters_out = it;

@@ -63,7 +63,9 @@ def main():
             f.write(f"{ns / 1e3:10.1f} us  {name}\n")
         f.write("```\n")
     # ---- full capture
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # `rep` is an .ncu-rep, or the CSV of its raw page exported on the GPU box (`ncu -i rep --page raw --csv`): the reports of
+    # the large-batch captures are too big to bring back whole
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     hdr = rr[0]
     traffic = {}
