@@ -68,7 +68,7 @@ def main():
     raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     hdr = rr[0]
-    traffic = {}
+    traffic, pipes = {}, {}
     with open(os.path.join(out_dir, f"{tag}_ncu_summary.md"), "w") as f:
         f.write(f"# {tag}: `ncu --set full --clock-control none` of the two hot kernels ({workload})\n\n")
         for r in rr[2:]:
@@ -85,11 +85,23 @@ def main():
                 return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
             tb = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
             traffic[name] = tb
+            pipes[name] = {k: float(vals[k][0]) for k in ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+                                                          "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                                                          "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                                                          "sm__warps_active.avg.pct_of_peak_sustained_active",
+                                                          "lts__t_sector_hit_rate.pct") if k in vals}
             f.write(f"\nDRAM traffic per launch: {tb / 1e6:.1f} MB\n\n")
     if is_bench:
-        qp = next(v for k, v in traffic.items() if "qp_kernel" in k)
-        json.dump({"kernel": "qp_kernel<17,6,1>", "dram_bytes_per_launch": qp, "source": f"profiles/{tag}_ncu_summary.md",
-                   "workload": workload}, open(os.path.join(out_dir, "qp_kernel_traffic.json"), "w"), indent=1)
+        qk = next(k for k in traffic if "qp_kernel" in k)
+        pp = pipes[qk]
+        json.dump({"kernel": "qp_kernel<17,6,1,2,1,false>", "dram_bytes_per_launch": traffic[qk], "source": f"profiles/{tag}_ncu_summary.md",
+                   "workload": workload,
+                   "sm__pipe_fp64_cycles_active_pct": pp.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "sm__pipe_tensor_cycles_active_pct": pp.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "smsp__issue_active_pct": pp.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "sm__warps_active_pct": pp.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                   "lts__t_sector_hit_rate_pct": pp.get("lts__t_sector_hit_rate.pct")},
+                  open(os.path.join(out_dir, "qp_kernel_traffic.json"), "w"), indent=1)
     print(open(os.path.join(out_dir, f"{tag}_launches.md")).read())
     print(open(os.path.join(out_dir, f"{tag}_ncu_summary.md")).read()[:3000])
 
