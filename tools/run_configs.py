@@ -84,6 +84,9 @@ def active_set(mpc, X, U, wide_x=False):
 def timed_solves(mpc, x0, yref, trim, steps, warmup, want_traj=False, keep=None):
     """steps timed solves of the local shard from the same cold iterate; returns (mean ms, last outputs)."""
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # inputs resident in HBM before the timed region (config 3's per-stage yref is 0.5 GB: converting it inside the timed events
+    # added a pageable host-to-device copy of 40 ... 150 ms to every step of the round-1 and first round-2 tables)
+    x0, yref, trim = (torch.as_tensor(a, dtype=torch.float64, device="cuda") for a in (x0, yref, trim))
     ts, out = [], None
     for i in range(warmup + steps):
         mpc.reset(x0, trim)
