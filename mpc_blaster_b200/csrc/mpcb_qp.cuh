@@ -667,6 +667,9 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 }
             }
             T Lu[NU], invd[NU];
+            // latency variant only.  Re-measured in round 2 with the tensor-core Gram (profiles/r02_ab_tp_hybrid.txt): in the
+            // single-buffer throughput variant the hybrid gains 4 % at 4,096 instances (2.3 waves) and loses 0.5 % at 6,144,
+            // 5.6 % at 16,384 and 8 % at 65,536 -- at 12 warps per SM the unrolled Cholesky competes for the instruction cache
             constexpr bool kGramFactor = (NSLOT == 2) && (MPCB_GRAM_MU < 1e29);
             if (kGramFactor && mu > T(MPCB_GRAM_MU) && mu <= (T)P.ipm_mu0) {
             // Early interior-point iterations (mu > MPCB_GRAM_MU): the normal-equations form, as HPIPM's default

@@ -31,3 +31,20 @@ for variant in (17, 12):
     torch.cuda.synchronize()
     print("qp8", variant, st.tolist(), mpc.iters.tolist())
 print("done")
+# round 2: reference-semantics instantiation (explicit norms + iterative refinement), SQP to convergence (NLP residual and
+# bookkeeping kernels), and the debug export of the QP / interior-point iterate
+for variant in (17, 12):
+    nx, nu = (17, 6) if variant == 17 else (12, 4)
+    x0, yref = sc.random_setpoints(6, seed=9, nx=nx, nu=nu)
+    mpc = BlasterMPC.canonical(N=6, batch=6, variant=variant, strict_reference=True)
+    mpc.reset(x0, sc.hover_trim(nu))
+    u0, X, U, st = mpc.solve(x0, yref)
+    d = mpc.debug_qp()
+    torch.cuda.synchronize()
+    print("strict", variant, st.tolist(), mpc.iters.tolist(), float(d["z"].abs().max()))
+    mpc2 = BlasterMPC.canonical(N=6, batch=6, variant=variant)
+    mpc2.reset(x0, sc.hover_trim(nu))
+    u0, X, U, st = mpc2.solve(x0, yref, sqp_iters=20, sqp_tol=1e-6)
+    torch.cuda.synchronize()
+    print("sqp", variant, st.tolist(), mpc2.sqp_iters.tolist(), mpc2.nlp_res.max(dim=0).values.tolist())
+print("done round 2")

@@ -27,7 +27,30 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
+def raw_only(name, csv_path, workload):
+    """`--raw-only <name> <raw.csv> "workload"`: summary of a capture whose report stayed on the GPU box."""
+    rr = list(csv.reader(open(csv_path)))
+    hdr = rr[0]
+    with open(os.path.join(ROOT, "profiles", f"{name}_ncu_summary.md"), "w") as f:
+        f.write(f"# {name}: `ncu --set full --clock-control none` ({workload})\n\n")
+        for r in rr[2:]:
+            kn = r[hdr.index("Kernel Name")].split("(")[0]
+            f.write(f"## `{kn}`\n\n| metric | unit | value |\n|---|---|---:|\n")
+            vals = {}
+            for i, h in enumerate(hdr):
+                if h in KEYS or ("pcsamp_warps_issue_stalled" in h and "not_issued" not in h):
+                    f.write(f"| {h} | {rr[1][i]} | {r[i]} |\n")
+                    vals[h] = (r[i], rr[1][i])
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+            tb = sum(float(vals[k][0]) * mult[vals[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            f.write(f"\nDRAM traffic per launch: {tb / 1e6:.1f} MB\n\n")
+            print(name, kn, f"{float(vals['gpu__time_duration.sum'][0]):.3f} {vals['gpu__time_duration.sum'][1]}", f"DRAM {tb / 1e9:.2f} GB",
+                  "L2 hit", vals.get("lts__t_sector_hit_rate.pct", ("?",))[0], "issue", vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", ("?",))[0])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--raw-only":
+        return raw_only(*sys.argv[2:5])
     args = [a for a in sys.argv[1:] if a != "--bench"]
     is_bench = "--bench" in sys.argv[1:]
     tag, launches, rep = args[:3]
