@@ -302,8 +302,8 @@ def run_gpu(args):
     zero_iterate = {"value": B / (float(np.mean(zms)) * 1e-3), "unit": UNIT + " per GPU", "ms_per_step": float(np.mean(zms)),
                     "mean_ipm_iters": float(mpc.iters.double().mean().item()), "max_ipm_iters": int(mpc.iters.max().item()),
                     "converged_frac": float((zst == 0).double().mean().item()),
-                    "note": "first solve from the all-zero iterate: the linearisation point violates x_0 = x0 by metres, so "
-                            "part of the batch has an infeasible linearised QP (status 3) and the rest needs more iterations"}
+                    "note": "first solve from the all-zero iterate (acados' default when nothing is set): the linearisation point is "
+                            "the origin, metres away from x0"}
     fp64_peak_early = mpc.fp64_peak_tflops()
     del mpc
 
