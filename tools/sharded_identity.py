@@ -25,6 +25,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=1000)
     ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--default-selection", action="store_true",
+                    help="let the scheduler pick the kernel variant by chunk size on both sides: reports the largest deviation instead of requiring identity")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     ngpu = torch.cuda.device_count()
@@ -39,7 +41,11 @@ def main():
     x0_h, yref_h = sc.random_setpoints(B, seed=99)
     trim = torch.as_tensor(sc.hover_trim(), device=dev)
     lo, hi = shard_range(B, rank, world)
-    mpc = BlasterMPC.canonical(N=N, batch=hi - lo, device=dev)
+    # Bit-identity is a statement about the SAME arithmetic on shards and on the whole batch: the host scheduler picks the QP
+    # kernel variant from the chunk size (latency / single-buffer / four-instances-per-warp: different summation orders,
+    # results equal to ~1e-9, tests/test_gpu_parity.py), so both sides pin the variant the shards would get by default.
+    pin = dict(throughput_batch=1 << 30, qp8_batch=1 << 30) if not a.default_selection else {}
+    mpc = BlasterMPC.canonical(N=N, batch=hi - lo, device=dev, **pin)
     mpc.reset(torch.as_tensor(x0_h[lo:hi], device=dev), trim)
     gdev = dev if nccl else torch.device("cpu")
 
@@ -61,16 +67,21 @@ def main():
     ok = True
     rep = None
     if rank == 0:
-        whole = BlasterMPC.canonical(N=N, batch=B, device=dev)
+        whole = BlasterMPC.canonical(N=N, batch=B, device=dev, **pin)
         whole.reset(torch.as_tensor(x0_h, device=dev), trim)
         xw = torch.as_tensor(x0_h, device=dev)
         conv = 1.0
+        dev_max = 0.0
         for step in range(2):
             uw, _, _, sw = whole.solve(xw, torch.as_tensor(yref_h, device=dev), want_traj=False)
-            ok = ok and torch.equal(uw.cpu(), outs[step][0]) and torch.equal(sw.cpu(), outs[step][1])
+            same = torch.equal(uw.cpu(), outs[step][0]) and torch.equal(sw.cpu(), outs[step][1])
+            good = (sw.cpu() == 0) & (outs[step][1] == 0)
+            dev_max = max(dev_max, float((uw.cpu()[good] - outs[step][0][good]).abs().max()))
+            ok = ok and (same if not a.default_selection else (torch.equal(sw.cpu(), outs[step][1]) and dev_max < 1e-6))
             conv = min(conv, float((sw == 0).double().mean()))
             xw = whole.step_plant(xw, uw)
-        rep = {"identical": bool(ok), "world": world, "backend": "nccl" if nccl else "gloo (ranks share one GPU)", "gpus": ngpu,
+        rep = {"identical": bool(ok) and not a.default_selection, "kernel_variant": "scheduler default on both sides" if a.default_selection else "pinned (one-instance latency kernel)",
+               "max_abs_du0": dev_max, "status_equal": bool(ok), "world": world, "backend": "nccl" if nccl else "gloo (ranks share one GPU)", "gpus": ngpu,
                "global_batch": B, "horizon": N, "control_steps": 2, "converged_frac": conv,
                "shards": [list(shard_range(B, g, world)) for g in range(world)]}
         print(json.dumps(rep), flush=True)
