@@ -20,6 +20,8 @@ ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--steps", type=int, default=500)
 ap.add_argument("--horizon", type=int, default=20)
 ap.add_argument("--check", type=int, default=0, help="instances to check against the C oracle (first steps only)")
+ap.add_argument("--max-fail-frac", type=float, default=1e-4,
+                help="fail if more than this fraction of all solves reports a non-zero status (a failed solve applies the stale u0, include/mpcb.h)")
 a = ap.parse_args()
 
 B, S, N = a.batch, a.steps, a.horizon
@@ -37,6 +39,7 @@ out = dict(config="closed-loop Monte-Carlo", batch=B, steps=S, horizon=N, second
            mean_ipm_iters=float(iters.double().mean() / S), mean_final_position_error_m=err,
            kernel_launches=mpc.kernel_launches())
 print(json.dumps(out), flush=True)
+assert out["failed_solves"] <= a.max_fail_frac * B * S, f"{out['failed_solves']} failed solves of {B * S}"
 
 if a.check:
     from oracle import blaster_oracle as bo, c_oracle as co
@@ -52,7 +55,8 @@ if a.check:
         orc.X[:], orc.U[:] = Xg.cpu().numpy(), Ug.cpu().numpy()
         u0, X, U, st = g.solve(x, yref[:C])
         uo, Xo, Uo, sto = orc.solve(x, yref[:C])
-        ok = (sto == 0) & (st.cpu().numpy() == 0)
+        assert (st.cpu().numpy() == sto).all(), (s, st.cpu().numpy(), sto)
+        ok = sto == 0
         worst = max(worst, float(np.abs(U.cpu().numpy()[ok] - Uo[ok]).max()), float(np.abs(X.cpu().numpy()[ok] - Xo[ok]).max()))
         x = g.step_plant(x, u0).cpu().numpy()
     print(json.dumps(dict(check_instances=C, check_steps=10, max_abs_diff_vs_oracle=worst)), flush=True)
