@@ -1141,4 +1141,14 @@ int mpcb_poc_jacobians(const double *euler, const double *motor, const double *p
     return 0;
 }
 
+#ifdef MPCB_PHASE_CLOCKS
+// experiment build only (tools/phase_clocks.py)
+int mpcb_debug_phase_clocks(unsigned long long *out16, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
 }  // extern "C"

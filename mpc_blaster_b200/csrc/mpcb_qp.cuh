@@ -38,6 +38,17 @@ namespace mpcb {
 #ifndef MPCB_DMMA
 #define MPCB_DMMA 1
 #endif
+#if defined(MPCB_PHASE_CLOCKS) && !defined(MPCB_HOST_EMU)
+// experiment build only (tools/phase_clocks.py): cycles per phase of the one-instance kernel, summed over warps
+__device__ unsigned long long g_phase_clk[16];
+#define MPCB_PH(i) do { if (lane == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_clk[i], (unsigned long long)(t_ - ph_t)); ph_t = t_; } } while (0)
+#define MPCB_PH_COUNT(i) do { if (lane == 0) atomicAdd(&g_phase_clk[i], 1ull); } while (0)
+#define MPCB_PH_INIT long long ph_t = clock64()
+#else
+#define MPCB_PH(i)
+#define MPCB_PH_COUNT(i)
+#define MPCB_PH_INIT
+#endif
 constexpr double kMuDiverge = 1e2;  // infeasibility test: mu > kMuDiverge * mu0 (the CPU checkers apply the same test; no feasible instance of the test scenarios exceeds 3 * mu0)
 
 // Per-warp shared memory: two stage-record images (same offsets as the global record) plus
@@ -137,13 +148,26 @@ MPCB_DEV void load_box(BoxIn<T, FBN> &in, const T *__restrict__ ws, int k0, int 
     }
 }
 
-// t2 = P r + p with P = Lxx Lxx' (Lxx in shared memory, zero upper triangle);
-// r in sm.sRb, p in sm.cPv, result in sm.sT2.
+// t2 = P r + p; r in sm.sRb, p in sm.cPv, result in sm.sT2.  sm.Lxx holds the factor of P (P = Lxx Lxx', zero upper
+// triangle) or -- PFORM, the normal-equations iterations of the latency variant -- the symmetric matrix P itself.
 template <int NX, int NU, typename T, int NSLOT>
-MPCB_DEV void apply_P(QpSmem<NX, NU, T, NSLOT> &sm)
+MPCB_DEV void apply_P(QpSmem<NX, NU, T, NSLOT> &sm, bool pform)
 {
     const int lane = lane_id();
     const int c = lane < NX ? lane : 0;
+    if (pform) {
+        T b0 = sm.cPv[c], b1 = T(0), b2 = T(0), b3 = T(0);
+        MPCB_UNROLL
+        for (int j = 0; j + 3 < NX; j += 4) {
+            b0 += sm.Lxx[c * NX + j] * sm.sRb[j]; b1 += sm.Lxx[c * NX + j + 1] * sm.sRb[j + 1];
+            b2 += sm.Lxx[c * NX + j + 2] * sm.sRb[j + 2]; b3 += sm.Lxx[c * NX + j + 3] * sm.sRb[j + 3];
+        }
+        MPCB_UNROLL
+        for (int j = NX & ~3; j < NX; j++) b0 += sm.Lxx[c * NX + j] * sm.sRb[j];
+        if (lane < NX) sm.sT2[lane] = (b0 + b1) + (b2 + b3);
+        warp_sync();
+        return;
+    }
     T a0 = T(0), a1 = T(0);
     MPCB_UNROLL
     for (int j = 0; j + 1 < NX; j += 2) {
@@ -187,7 +211,7 @@ MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
 // and for the affine sweep the sums that give mu_aff(alpha) plus the corrector gradient pieces.
 template <int NX, int NU, typename T, int NSLOT, bool FINAL>
 MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, StagePipe &pipe, T *__restrict__ ws, T sigmu, T &imax_out,
-                            T &acc1_out, T &acc2_out)
+                            T &acc1_out, T &acc2_out, bool pform = false)
 {
     using L = Layout<NX, NU>;
     constexpr int NZ = L::NZ;
@@ -299,7 +323,21 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
             }
         }
         warp_sync();
-        if (FINAL) {
+        if (FINAL && pform) {
+            // dpi_{k+1} = P_{k+1} dx_{k+1} + p_{k+1} with the matrix P itself in the record (normal-equations iterations)
+            const int c = lane < NX ? lane : 0;
+            const T *Px = s + L::O_LXX + c * NX;
+            T b0 = s[L::O_PV + c], b1 = T(0), b2 = T(0), b3 = T(0);
+            MPCB_UNROLL
+            for (int j = 0; j + 3 < NX; j += 4) {
+                b0 += Px[j] * sm.sRb[j]; b1 += Px[j + 1] * sm.sRb[j + 1];
+                b2 += Px[j + 2] * sm.sRb[j + 2]; b3 += Px[j + 3] * sm.sRb[j + 3];
+            }
+            MPCB_UNROLL
+            for (int j = NX & ~3; j < NX; j++) b0 += Px[j] * sm.sRb[j];
+            if (lane < NX) wk[L::STAGE + L::O_DPI + lane] = (b0 + b1) + (b2 + b3);
+            warp_sync();
+        } else if (FINAL) {
             const int c = lane < NX ? lane : 0;
             const T *Lx = s + L::O_LXX;
             T a0 = T(0), a1 = T(0);
@@ -336,7 +374,7 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
 // increment (ddu_k = -Luu^{-T}(d lvec_k + Lxu' ddx_k), ddx_{k+1} = [B A] ddz_k, ddpi_{k+1} = P_{k+1} ddx_{k+1} + d p_{k+1}),
 // ADDS it to dz / dpi in the records and redoes the box step-length computation of the corrected step.
 template <int NX, int NU, typename T, int NSLOT>
-MPCB_DEV void refine_forward(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__restrict__ ws, T sigmu, T &imax_out)
+MPCB_DEV void refine_forward(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__restrict__ ws, T sigmu, T &imax_out, bool pform)
 {
     using L = Layout<NX, NU>;
     constexpr int NZ = L::NZ;
@@ -401,9 +439,11 @@ MPCB_DEV void refine_forward(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *_
         const int c = lane < NX ? lane : 0;
         const T *Lx = wk + L::STAGE + L::O_LXX;
         T t1 = T(0);
-        MPCB_UNROLL4
-        for (int j = 0; j < NX; j++) t1 += Lx[j * NX + c] * sm.sRb[j];
-        if (lane < NX) sm.sT1[lane] = t1;
+        if (!pform) {
+            MPCB_UNROLL4
+            for (int j = 0; j < NX; j++) t1 += Lx[j * NX + c] * sm.sRb[j];
+        }
+        if (lane < NX) sm.sT1[lane] = pform ? sm.sRb[lane] : t1;  // P-form: the record holds P itself, one product
         warp_sync();
         T t2 = wk[L::STAGE + L::O_C1 + NU + c];
         MPCB_UNROLL4
@@ -495,6 +535,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
     int status = ST_MAXITER, it = 0;
     pipe_fence();  // the QP data written above is fetched by the bulk-copy pipeline below
     warp_sync();
+    MPCB_PH_INIT;
 
     for (it = 0; it < P.ipm_max_iter; it++) {
         if (!(est_g == est_g) || !(est_b == est_b) || !(mu == mu)) { status = ST_NAN; break; }
@@ -511,6 +552,20 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
         // bound slacks (xd) always -- est_b / est_d of the next test are these MEASURED values times (1 - alpha), not an
         // extrapolation from the cold start -- stationarity (xg) in the STRICT instantiation only
         T xg = T(0), xb = T(0), xd = T(0);
+        // latency variant only (both measured on the single-buffer throughput variant, 168-register cap, 12 warps per SM:
+        // tensor-core products 0.4 .. 1 % slower, profiles/r02_ab_dmma_tp.txt; hybrid factorisation +4 % at 4,096 instances,
+        // -0.5 % at 6,144, -5.6 % at 16,384, -8 % at 65,536, profiles/r02_ab_tp_hybrid.txt)
+        constexpr bool kDmma = (NSLOT == 2) && (MPCB_DMMA != 0);
+        constexpr bool kGramFactor = (NSLOT == 2) && (MPCB_GRAM_MU < 1e29);
+        // this iteration factorises in normal-equations form (early iterations, see the stage loop) ...
+        const bool gram_it = kGramFactor && mu > T(MPCB_GRAM_MU) && mu <= (T)P.ipm_mu0;
+        // ... and then carries P_k itself from stage to stage instead of its Cholesky factor (sm.Lxx, the Lxx field of
+        // the records): the classical Riccati recursion.  Only the NU input pivots are eliminated; what is left in the
+        // state rows is P_k, which the next stage needs only inside [B A]' P_k [B A] -- its factor would be multiplied
+        // back together there.  17 of the 23 pivots of the dependent chain (store -> sync -> load -> rsqrt -> FMA) go.
+        const bool pform = kDmma && gram_it;
+        MPCB_PH(0);
+        MPCB_PH_COUNT(11);
         // ================= S1: backward sweep -- residuals, factorisation, affine right-hand side
         // record k: run A = [BAt], run B = [z tl tu ll lu lb ub g pi b]
         constexpr int RUNB = L::O_C1 - L::O_Z;
@@ -531,10 +586,9 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 const T zN = wN[L::O_Z + lane], piN = wN[L::O_PI + i];
                 const T q = H0 * zN + wN[L::O_G + lane] - piN;
                 if (STRICT) xg = fmax(xg, fabs(q));
-                sm.Lxx[i * NX + i] = sqrt(H0);
+                // (the whole row: a P-form iteration leaves a full symmetric matrix behind, the factor form needs the zero upper triangle)
                 MPCB_UNROLL
-                for (int c = 0; c < NX; c++)
-                    if (c < i) sm.Lxx[i * NX + c] = T(0);
+                for (int c = 0; c < NX; c++) sm.Lxx[i * NX + c] = (c == i) ? (pform ? H0 : sqrt(H0)) : T(0);
                 sm.cPv[i] = q;
                 sm.cPi[i] = piN;
                 sm.cZx[i] = zN;
@@ -586,9 +640,6 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     q += (ll + ll * rdl * itl) - (lu + lu * rdu * itu);
                 }
             }
-            // latency variant only: measured on the single-buffer throughput variant (168-register cap, Householder LQ on every
-            // iteration, so only the W product moves) it is 0.4 .. 1 % slower (profiles/r02_ab_dmma_tp.txt)
-            constexpr bool kDmma = (NSLOT == 2) && (MPCB_DMMA != 0);
             if (kDmma && lane < NZ) sm.hd[lane] = Hd;  // read back per tile after the Gram product (a warp_sync lies between)
             // r_k = b_k + [B A] z_k - dx-part of z_{k+1}
             if (lane < NX) {
@@ -609,7 +660,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             }
             warp_sync();
             // t2 = P_{k+1} r_k + p_{k+1}
-            apply_P<NX, NU, T, NSLOT>(sm);
+            apply_P<NX, NU, T, NSLOT>(sm, pform);
             // carry this stage's pi and dx-part of z to stage k-1 (cPi / cZx were consumed above)
             if (lane < NX) { sm.cPi[lane] = s[L::O_PI + lane]; sm.cZx[lane] = s[L::O_Z + NU + lane]; }
             // affine backward vector before the substitution: l = q + [B A]' t2 (the last use of this lane's row of [B A]')
@@ -634,29 +685,33 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 static_for<0, NI>([&](auto I_) {
                     static_for<0, NJ>([&](auto J_) { wt[decltype(I_)::value][decltype(J_)::value][0] = T(0); wt[decltype(I_)::value][decltype(J_)::value][1] = T(0); });
                 });
-                static_for<0, NS>([&](auto S_) {
-                    constexpr int st = decltype(S_)::value;
-                    const int kk = 4 * st + tq;       // row of Lxx = column of [B A]' of this lane's fragments
-                    const bool kin = kk < NX;
-                    T af[NI];
-                    static_for<0, NI>([&](auto I_) {
-                        constexpr int I = decltype(I_)::value;
-                        const int row = 8 * I + tg;
-                        const bool in = kin && row < NZ;
-                        const T v = s[L::O_BAT + (in ? row * L::LDB + kk : 0)];
-                        af[I] = in ? v : T(0);
+                auto wprod = [&](auto FULL_) {
+                    constexpr bool FULL = decltype(FULL_)::value != 0;  // P form: sm.Lxx is the full symmetric P_{k+1}, no tile is skipped
+                    static_for<0, NS>([&](auto S_) {
+                        constexpr int st = decltype(S_)::value;
+                        const int kk = 4 * st + tq;       // row of Lxx = column of [B A]' of this lane's fragments
+                        const bool kin = kk < NX;
+                        T af[NI];
+                        static_for<0, NI>([&](auto I_) {
+                            constexpr int I = decltype(I_)::value;
+                            const int row = 8 * I + tg;
+                            const bool in = kin && row < NZ;
+                            const T v = s[L::O_BAT + (in ? row * L::LDB + kk : 0)];
+                            af[I] = in ? v : T(0);
+                        });
+                        static_for<0, NJ>([&](auto J_) {
+                            constexpr int J = decltype(J_)::value;
+                            if constexpr (FULL || 8 * J <= 4 * st + 3) {  // some row of this k-step reaches the tile's columns (Lxx[j][c] = 0 for c > j)
+                                const int col = 8 * J + tg;
+                                const bool in = kin && col < NX;
+                                const T v = sm.Lxx[in ? kk * NX + col : 0];
+                                const T bf = in ? v : T(0);
+                                static_for<0, NI>([&](auto I_) { constexpr int I = decltype(I_)::value; warp_dmma(wt[I][J][0], wt[I][J][1], af[I], bf); });
+                            }
+                        });
                     });
-                    static_for<0, NJ>([&](auto J_) {
-                        constexpr int J = decltype(J_)::value;
-                        if constexpr (8 * J <= 4 * st + 3) {  // some row of this k-step reaches the tile's columns (Lxx[j][c] = 0 for c > j)
-                            const int col = 8 * J + tg;
-                            const bool in = kin && col < NX;
-                            const T v = sm.Lxx[in ? kk * NX + col : 0];
-                            const T bf = in ? v : T(0);
-                            static_for<0, NI>([&](auto I_) { constexpr int I = decltype(I_)::value; warp_dmma(wt[I][J][0], wt[I][J][1], af[I], bf); });
-                        }
-                    });
-                });
+                };
+                if (pform) wprod(IntC<1>{}); else wprod(IntC<0>{});
             } else {
                 MPCB_UNROLL
                 for (int c = 0; c < NX; c++) {
@@ -667,11 +722,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 }
             }
             T Lu[NU], invd[NU];
-            // latency variant only.  Re-measured in round 2 with the tensor-core Gram (profiles/r02_ab_tp_hybrid.txt): in the
-            // single-buffer throughput variant the hybrid gains 4 % at 4,096 instances (2.3 waves) and loses 0.5 % at 6,144,
-            // 5.6 % at 16,384 and 8 % at 65,536 -- at 12 warps per SM the unrolled Cholesky competes for the instruction cache
-            constexpr bool kGramFactor = (NSLOT == 2) && (MPCB_GRAM_MU < 1e29);
-            if (kGramFactor && mu > T(MPCB_GRAM_MU) && mu <= (T)P.ipm_mu0) {
+            MPCB_PH(1);
+            if (gram_it) {
             // Early interior-point iterations (mu > MPCB_GRAM_MU): the normal-equations form, as HPIPM's default
             // Riccati -- M = diag(Hd) + W W' formed row by row (lane i owns row i, the rows of W broadcast from
             // shared memory), then a right-looking Cholesky, fully unrolled so that row i stays in registers: per
@@ -693,10 +745,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 MPCB_UNROLL
                 for (int c = 0; c <= NZ; c++) m[c] = T(0);
                 if constexpr (kDmma) {
-                    // Gram matrix on the tensor cores.  M = W W' contracts over the columns of W, and ANY assignment of columns
-                    // to k-indices is a valid contraction as long as A and B use the same one: lane (g, q) feeds the
-                    // entries of W it already holds -- W[8 I + g][8 Jc + 2 q + h] as A, W[8 J + g][8 Jc + 2 q + h] as B -- so
-                    // the k-steps run over (Jc, h) with no data movement at all: NI (NI + 1) / 2 x 2 NJ DMMAs (36, BLASTER17).
+                    // M = T [B A] with T = [B A]' P_{k+1} in the accumulator registers (the product above).  The contraction runs
+                    // over the columns of T, and ANY assignment of columns to k-indices is valid as long as A and B use the same
+                    // one: lane (g, q) feeds T[8 I + g][8 Jc + 2 q + h], which it holds, as A, and loads
+                    // [B A]'[8 J + g][8 Jc + 2 q + h] from the record image as B -- the k-steps run over (Jc, h).
+                    // NI (NI + 1) / 2 tiles x the k-steps that reach a column < NX (30 DMMAs, BLASTER17).
                     T mt[NI][NI][2];
                     static_for<0, NI>([&](auto I_) {
                         static_for<0, NI>([&](auto J_) { mt[decltype(I_)::value][decltype(J_)::value][0] = T(0); mt[decltype(I_)::value][decltype(J_)::value][1] = T(0); });
@@ -705,13 +758,25 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                         constexpr int Jc = decltype(C_)::value;
                         static_for<0, 2>([&](auto H_) {
                             constexpr int h = decltype(H_)::value;
-                            static_for<0, NI>([&](auto I_) {
-                                constexpr int I = decltype(I_)::value;
-                                static_for<0, I + 1>([&](auto J_) {
+                            if constexpr (8 * Jc + h < NX) {
+                                const int kk = 8 * Jc + 2 * tq + h;
+                                const bool kin = kk < NX;
+                                T bq[NI];
+                                static_for<0, NI>([&](auto J_) {
                                     constexpr int J = decltype(J_)::value;
-                                    warp_dmma(mt[I][J][0], mt[I][J][1], wt[I][Jc][h], wt[J][Jc][h]);
+                                    const int row = 8 * J + tg;
+                                    const bool in = kin && row < NZ;
+                                    const T v = s[L::O_BAT + (in ? row * L::LDB + kk : 0)];
+                                    bq[J] = in ? v : T(0);
                                 });
-                            });
+                                static_for<0, NI>([&](auto I_) {
+                                    constexpr int I = decltype(I_)::value;
+                                    static_for<0, I + 1>([&](auto J_) {
+                                        constexpr int J = decltype(J_)::value;
+                                        warp_dmma(mt[I][J][0], mt[I][J][1], wt[I][Jc][h], bq[J]);
+                                    });
+                                });
+                            }
                         });
                     });
                     // tiles -> rows: block I (rows 8 I .. 8 I + 7) is stored with 8 (I + 1) columns at an even, padded stride
@@ -784,10 +849,24 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     else { if (lane >= j && lane < NZ) sm.Lxx[(lane - NU) * NX + (j - NU)] = val; }
                 };
                 static_for<0, NU>(pivot);
-                if (k > 0) static_for<NU, NZ>(pivot);
+                if constexpr (kDmma) {
+                    // P form: after the input pivots the state rows hold the Schur complement P_k (lower part valid); it
+                    // replaces P_{k+1} in shared memory as a full symmetric matrix (the products above are done with it)
+                    if (k > 0 && lane >= NU && lane < NZ) {
+                        const int i = lane - NU;
+                        static_for<0, NX>([&](auto C_) {
+                            constexpr int c = decltype(C_)::value;
+                            if (c <= i) { sm.Lxx[i * NX + c] = m[NU + c]; sm.Lxx[c * NX + i] = m[NU + c]; }
+                        });
+                    }
+                } else {
+                    if (k > 0) static_for<NU, NZ>(pivot);
+                }
                 last_sig = sig;
             }
             warp_sync();
+            MPCB_PH(2);
+            MPCB_PH_COUNT(9);
             } else {
             const T dsq = sqrt(Hd);
             if (lane < NZ) { sm.hd[lane] = Hd; sm.ds[lane] = dsq; }  // visible after the first pivot's warp_sync
@@ -873,6 +952,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
 
             MPCB_UNROLL
             for (int c = 0; c < NU; c++) { Lu[c] = sm.Lcol[(lane < NZ ? lane : 0) * L::NUP + c]; invd[c] = sm.Linv[c]; }
+            MPCB_PH(3);
+            MPCB_PH_COUNT(10);
             }
             const T l = fwd_subst<NU, T>(lin, Lu, invd, NZ);
             if (lane < NU) wk[L::O_LVEC + lane] = l;
@@ -890,6 +971,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             warp_sync();
             if (k > 0)
                 for (int idx = lane; idx < NX * NX; idx += 32) wk[L::O_LXX + idx] = sm.Lxx[idx];
+            MPCB_PH(4);
         }
         pipe_fence();  // L, lvec, r_b, p written by this sweep are fetched by the next ones
         warp_sync();
@@ -915,6 +997,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             sigma = sigma * sigma * sigma;
             sigmu = sigma * mu;
         }
+        MPCB_PH(5);
 
         // ================= S3: backward sweep for the corrector increment (delta form)
         // record k: [BAt | Lu | invd | lvec] and [c1 c2]; pv_k is read-modify-written in global memory.
@@ -977,16 +1060,18 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             warp_sync();
         };
         corrector_sweep(IntC<0>{});
+        MPCB_PH(6);
 
         // ================= S4: forward sweep, full predictor-corrector step (+ dpi, + step length)
         T alpha;
         {
             T imax, d1, d2;
-            forward_sweep<NX, NU, T, NSLOT, true>(P, sm, pipe, ws, sigmu, imax, d1, d2);
+            forward_sweep<NX, NU, T, NSLOT, true>(P, sm, pipe, ws, sigmu, imax, d1, d2, pform);
             // alpha = min(1, max(0.995, 1 - mu_aff) * alpha_max)
             const T tau = fmax(T(0.995), T(1) - mu_aff);
             alpha = (imax > tau) ? tau / imax : T(1);
         }
+        MPCB_PH(7);
         if (STRICT) {
             // ================= R: one step of iterative refinement on the step just computed (HPIPM: itref_corr_max).
             // The residual of the stationarity rows of the reduced Newton system,
@@ -1029,7 +1114,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             warp_sync();
             corrector_sweep(IntC<1>{});
             T imax;
-            refine_forward<NX, NU, T, NSLOT>(P, sm, ws, sigmu, imax);
+            refine_forward<NX, NU, T, NSLOT>(P, sm, ws, sigmu, imax, pform);
             const T tau = fmax(T(0.995), T(1) - mu_aff);
             alpha = (imax > tau) ? tau / imax : T(1);
         }
@@ -1077,6 +1162,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
         est_d = xd * (T(1) - alpha);
         pipe_fence();
         warp_sync();
+        MPCB_PH(8);
         if (!(alpha >= (T)P.alpha_min)) {
             status = (alpha == alpha) ? ST_MINSTEP : ST_NAN;
             it++;
