@@ -34,7 +34,7 @@ typedef struct {
     int ipm_max_iter;
     int rg_mode; /* 0 stationarity residual tracked analytically, 1 recomputed from pi and used in the test, 2 recomputed for the
                     Newton right-hand side while the test uses the extrapolated norms, confirmed explicitly before success (the product's rule) */
-    int ric_alg; /* 0 Cholesky of Hd+WW', 1 Householder LQ of [sqrt(Hd) | W] */
+    int ric_alg; /* 0 Cholesky of Hd+WW', 1 Householder LQ of [sqrt(Hd) | W] (the checker), 3 experiment: classical recursion on P_k with the pinned directions kept in a side list (ric_factor_split) */
     double ipm_mu0, ipm_thr0, tol_stat, tol_eq, tol_ineq, tol_comp, alpha_min;
     int strict; /* reference semantics (mpcb_config.strict_reference): explicit residual norms in the stopping test (rg_mode 1
                    is then implied), no early exit on diverging multipliers, last iterate applied on max-iter */
@@ -51,6 +51,58 @@ static int orc_debug(void)
     static int flag = -1;
     if (flag < 0) flag = getenv("ORC_DEBUG") != NULL;
     return flag;
+}
+
+/* experiment ric_alg = 3 (tools/split_factor_viability.py): thresholds (squared column norm of a carried column; barrier
+ * diagonal of a state) and a histogram of the list length per stage factorisation */
+static double orc_huge_tau(void)
+{
+    static double tau = -1.0;
+    if (tau < 0.0) { const char *e = getenv("ORC_HUGE_TAU"); tau = e ? atof(e) : 1e6; }
+    return tau;
+}
+static double orc_huge_tau_d(void)
+{
+    static double tau = -1.0;
+    if (tau < 0.0) { const char *e = getenv("ORC_HUGE_TAU_D"); tau = e ? atof(e) : 1e6; }
+    return tau;
+}
+static double orc_split_mu(void) /* the experiment is used while mu > this (0 = every iteration) */
+{
+    static double v = -1.0;
+    if (v < 0.0) { const char *e = getenv("ORC_SPLIT_MU"); v = e ? atof(e) : 0.0; }
+    return v;
+}
+static int orc_huge_hmax(void) /* capacity of the list of carried columns */
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("ORC_HUGE_HMAX"); v = e ? atoi(e) : 34; if (v > 34) v = 34; }
+    return v;
+}
+static long orc_split_iters[2]; /* interior-point iterations factorised by the LQ / by the split recursion */
+static void orc_split_iter(int split)
+{
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    orc_split_iters[split]++;
+}
+void orc_split_iterations(long *out, int reset)
+{
+    out[0] = orc_split_iters[0]; out[1] = orc_split_iters[1];
+    if (reset) orc_split_iters[0] = orc_split_iters[1] = 0;
+}
+static long orc_huge_hist[36];
+static void orc_huge_count(int nh)
+{
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    orc_huge_hist[nh < 35 ? nh : 35]++;
+}
+void orc_huge_histogram(long *out, int reset)
+{
+    for (int i = 0; i < 36; i++) { out[i] = orc_huge_hist[i]; if (reset) orc_huge_hist[i] = 0; }
 }
 
 /* blastermodel.py:124,162-167: full 17-state model */

@@ -29,6 +29,8 @@ typedef struct {
     double *lvec; /* (N+1) * NZ : Luu^{-1} l_u (first NU) */
     double *Hd;   /* (N+1) * NZ diag Hessian + barrier */
     double *H0;   /* (N+1) * NZ diag Hessian */
+    int pform;    /* experiment ric_alg = 3: the xx block of L holds the full symmetric P_k, not its factor */
+    int split_off; /* experiment ric_alg = 3: the list of carried columns has overflowed in this solve -> LQ from now on */
 } SFX(ws_t);
 
 static size_t SFX(ws_doubles)(int N)
@@ -121,8 +123,125 @@ static void SFX(plant_step)(const orc_problem *P, const double *x, const double 
 /* ---- A6: backward Riccati factorisation in square-root form (HPIPM's default
  *      algorithm class):  M_k = diag(Hd_k) + BAt_k P_{k+1} BAt_k',  P_{k+1} = Lxx Lxx',
  *      L_k = chol(M_k) = [Luu 0; Lxu Lxx].  Returns 0, or 1 when a pivot is not positive. */
+/* Experiment ric_alg = 3 (tools/split_factor_viability.py; never the checker): the classical Riccati recursion on the
+ * matrix P_k itself (normal-equations form, input pivots only), made safe for numerically pinned states by keeping
+ * their contributions OUT of the matrix: P_k = P'_k + V_k V_k' with P'_k of ordinary size and V_k a short list of huge
+ * columns (sqrt(Hd_j) e_j for every state whose barrier diagonal exceeds tau_d, plus what earlier pins leave behind
+ * after the inputs have been eliminated).  Stage k: Cholesky of the input block of D + [B A]' P' [B A], then the
+ * columns [B A]' V are brought in by a Householder LQ update of the NU factor columns (the stable rank-h update);
+ * what the update leaves in the state rows is V_k.  Columns whose squared norm has dropped below tau are folded
+ * into P'.  The xx block of L then holds P_k in full (for the P r + p products of the solves). */
+static int SFX(ric_factor_split)(const orc_problem *P, SFX(ws_t) * w, int N)
+{
+    const double tau = orc_huge_tau(), tau_d = orc_huge_tau_d();
+    double Pp[NX][NX], V[NX + NX][NX];
+    int h = 0;
+    double *LN = w->L + (size_t)N * NZ * NZ;
+    for (int i = 0; i < NZ * NZ; i++) LN[i] = 0.0;
+    for (int i = 0; i < NX; i++)
+        for (int c = 0; c < NX; c++) Pp[i][c] = 0.0;
+    for (int i = 0; i < NX; i++) {
+        double d = w->Hd[(size_t)N * NZ + NU + i];
+        if (!(d > 0.0)) return 1;
+        Pp[i][i] = d;
+        LN[(NU + i) * NZ + NU + i] = d;
+    }
+    for (int k = N - 1; k >= 0; k--) {
+        const double *BAt = w->BAt + (size_t)k * NZ * NX;
+        double *L = w->L + (size_t)k * NZ * NZ;
+        double M[NZ][NZ], T[NZ][NX], Wh[NZ][NX + NX];
+        for (int i = 0; i < NZ; i++)
+            for (int c = 0; c < NX; c++) {
+                double acc = 0.0;
+                for (int j = 0; j < NX; j++) acc += BAt[i * NX + j] * Pp[j][c];
+                T[i][c] = acc;
+            }
+        for (int i = 0; i < NZ; i++)
+            for (int j = 0; j < NZ; j++) {
+                double acc = 0.0;
+                for (int c = 0; c < NX; c++) acc += T[i][c] * BAt[j * NX + c];
+                M[i][j] = acc;
+            }
+        int pin[NX], np = 0;
+        for (int i = 0; i < NZ; i++) {
+            const double d = w->Hd[(size_t)k * NZ + i];
+            if (!(d > 0.0)) return 1;
+            if (i >= NU && d > tau_d) pin[np++] = i - NU;
+            else M[i][i] += d;
+        }
+        for (int i = 0; i < NZ; i++)
+            for (int q = 0; q < h; q++) {
+                double acc = 0.0;
+                for (int c = 0; c < NX; c++) acc += BAt[i * NX + c] * V[q][c];
+                Wh[i][q] = acc;
+            }
+        for (int i = 0; i < NZ * NZ; i++) L[i] = 0.0;
+        for (int j = 0; j < NU; j++) {
+            double d = M[j][j];
+            if (!(d > 0.0)) return 1;
+            d = sqrt(d);
+            L[j * NZ + j] = d;
+            for (int i = j + 1; i < NZ; i++) L[i * NZ + j] = M[i][j] / d;
+            for (int i = j + 1; i < NZ; i++)
+                for (int c = j + 1; c < NZ; c++) M[i][c] -= L[i * NZ + j] * L[c * NZ + j];
+        }
+        if (h)
+            for (int j = 0; j < NU; j++) {
+                const double d = L[j * NZ + j];
+                double s2 = d * d;
+                for (int q = 0; q < h; q++) s2 += Wh[j][q] * Wh[j][q];
+                const double sig = sqrt(s2), v0 = d + sig, beta = 1.0 / (sig * v0);
+                L[j * NZ + j] = sig;
+                for (int i = j + 1; i < NZ; i++) {
+                    double dot = v0 * L[i * NZ + j];
+                    for (int q = 0; q < h; q++) dot += Wh[j][q] * Wh[i][q];
+                    const double f = beta * dot;
+                    L[i * NZ + j] = f * v0 - L[i * NZ + j];
+                    for (int q = 0; q < h; q++) Wh[i][q] -= f * Wh[j][q];
+                }
+            }
+        /* P'_k = Schur complement of the ordinary part; the list: what the update left in the state rows, and the new pins */
+        for (int i = 0; i < NX; i++)
+            for (int c = 0; c < NX; c++) Pp[i][c] = M[NU + i][NU + c];
+        int hn = 0;
+        double Vn[NX + NX][NX];
+        for (int q = 0; q < h; q++) {
+            double n2 = 0.0;
+            for (int i = 0; i < NX; i++) n2 += Wh[NU + i][q] * Wh[NU + i][q];
+            if (n2 > tau && hn + np >= orc_huge_hmax()) w->split_off = 1; /* overflow: this column is folded, later iterations use the LQ */
+            if (n2 > tau && hn + np < orc_huge_hmax()) {
+                for (int i = 0; i < NX; i++) Vn[hn][i] = Wh[NU + i][q];
+                hn++;
+            } else {
+                for (int i = 0; i < NX; i++)
+                    for (int c = 0; c < NX; c++) Pp[i][c] += Wh[NU + i][q] * Wh[NU + c][q];
+            }
+        }
+        for (int q = 0; q < np; q++) {
+            if (hn >= orc_huge_hmax()) { w->split_off = 1; Pp[pin[q]][pin[q]] += w->Hd[(size_t)k * NZ + NU + pin[q]]; continue; }
+            for (int i = 0; i < NX; i++) Vn[hn][i] = 0.0;
+            Vn[hn][pin[q]] = sqrt(w->Hd[(size_t)k * NZ + NU + pin[q]]);
+            hn++;
+        }
+        if (k > 0) orc_huge_count(hn);
+        h = hn;
+        for (int q = 0; q < h; q++)
+            for (int i = 0; i < NX; i++) V[q][i] = Vn[q][i];
+        for (int i = 0; i < NX; i++)
+            for (int c = 0; c < NX; c++) {
+                double acc = Pp[i][c];
+                for (int q = 0; q < h; q++) acc += V[q][i] * V[q][c];
+                L[(NU + i) * NZ + NU + c] = acc;
+            }
+    }
+    return 0;
+}
+
 static int SFX(ric_factor)(const orc_problem *P, SFX(ws_t) * w, int N, double mu)
 {
+    w->pform = 0;
+    if (P->ric_alg == 3 && !(mu > P->ipm_mu0) && mu > orc_split_mu() && !w->split_off) { w->pform = 1; orc_split_iter(1); return SFX(ric_factor_split)(P, w, N); }
+    if (P->ric_alg == 3) orc_split_iter(0);
     const int f32 = P->mixed_mu > 0.0 && mu > P->mixed_mu && mu <= P->ipm_mu0;
     double *LN = w->L + (size_t)N * NZ * NZ;
     for (int i = 0; i < NZ * NZ; i++) LN[i] = 0.0;
@@ -276,6 +395,12 @@ static void SFX(ric_solve)(SFX(ws_t) * w, int N)
             for (int c = 0; c <= i; c++) acc += Ln[(NU + i) * NZ + NU + c] * t1[c];
             t2[i] = acc;
         }
+        if (w->pform)
+            for (int i = 0; i < NX; i++) {
+                double acc = pn[i];
+                for (int c = 0; c < NX; c++) acc += Ln[(NU + i) * NZ + NU + c] * r[c];
+                t2[i] = acc;
+            }
         for (int i = 0; i < NZ; i++) {
             double acc = w->q[(size_t)k * NZ + i];
             for (int j = 0; j < NX; j++) acc += BAt[i * NX + j] * t2[j];
@@ -329,6 +454,10 @@ static void SFX(ric_solve)(SFX(ws_t) * w, int N)
         for (int i = 0; i < NX; i++) {
             double acc = w->pv[(size_t)(k + 1) * NX + i];
             for (int c = 0; c <= i; c++) acc += Ln[(NU + i) * NZ + NU + c] * t1[c];
+            if (w->pform) {
+                acc = w->pv[(size_t)(k + 1) * NX + i];
+                for (int c = 0; c < NX; c++) acc += Ln[(NU + i) * NZ + NU + c] * xn[c];
+            }
             w->dpi[(size_t)(k + 1) * NX + i] = acc;
         }
         for (int i = 0; i < NX; i++) dx[i] = xn[i];
@@ -439,6 +568,7 @@ static int SFX(ipm)(const orc_problem *P, SFX(ws_t) * w, int N, int *iters_out)
     }
     for (size_t i = 0; i < (size_t)(N + 1) * NX; i++) w->pi[i] = 0.0;
     int status = 2, it;
+    w->split_off = 0;
     double rg_est = 0.0, rb_est = 0.0, rd_est = 0.0;
     for (it = 0; it < P->ipm_max_iter; it++) {
         /* residuals */
