@@ -83,8 +83,9 @@ typedef struct mpcb_config {
      * Strict solves always run the one-instance-per-warp kernel. */
     int32_t strict_reference;
     /* Kernel selection by workspace-chunk size, 0 = measured defaults: chunks of at least
-     * throughput_batch instances use the single-buffer variant of the one-instance-per-warp kernel, chunks of at least
-     * qp8_batch the four-instances-per-warp kernel.  qp8_warps > 0 caps that kernel's grid (test hook). */
+     * qp8_batch instances (default 8,192 BLASTER17 / 4,096 QUAD12, QUAT13) use the four-instances-per-warp kernel, chunks
+     * of at least throughput_batch the single-buffer variant of the one-instance-per-warp kernel (default: never -- the
+     * latency variant is faster at every size measured since round 2).  qp8_warps > 0 caps the qp8 grid (test hook). */
     int32_t throughput_batch, qp8_batch, qp8_warps;
 } mpcb_config;
 

@@ -674,16 +674,17 @@ int mpcb_create(const mpcb_config *cfg, mpcb_handle **out)
     if (wsb > h->max_batch) wsb = h->max_batch;
     h->ws_batch = wsb;
     {
-        // Kernel selection by chunk size (mpcb_config fields; 0 = the measured defaults):
-        //  * throughput_batch: from ~2 waves of the latency variant (9 warps x 148 SMs) on, the single-buffer variant
-        //    (12 warps per SM) wins -- re-measured in round 2 with the hybrid factorisation in the latency variant:
-        //    331 k against 307 k solves/s at 4,096 BLASTER17 instances, 351 k against 307 k at 6,144;
+        // Kernel selection by chunk size (mpcb_config fields; 0 = the measured defaults, profiles/r02_crossover.txt):
+        //  * throughput_batch: the single-buffer variant (12 warps per SM) used to win from 4,096 instances on; since the
+        //    latency variant carries P_k in its normal-equations iterations (round 2) it no longer does at any size
+        //    measured (BLASTER17: 327 k against 378 k solves/s at 4,096, 346 k against 376 k at 6,144, 371 k against
+        //    384 k at 16,384) -- off by default, the field still forces it;
         //  * qp8_batch: the four-instances-per-warp kernel (persistent, groups refilled from a work counter, next
-        //    stage's record prefetched into L2) is faster from ~2,600 instances on for QUAD12 (576 k against 487 k
-        //    solves/s at 3,072) and from two of its waves (148 SMs x 7 warps x 4 = 4,144 instances each) on for
-        //    BLASTER17 (390 k against 362 k at 8,192; 460 k against 393 k at 65,536).
-        h->throughput_batch = cfg->throughput_batch > 0 ? cfg->throughput_batch : 4096;
-        h->qp8_batch = cfg->qp8_batch > 0 ? cfg->qp8_batch : (cfg->variant == 17 ? 8192 : 3072);
+        //    stage's record prefetched into L2) is faster from two of its waves (148 SMs x 7 warps x 4 = 4,144
+        //    instances each) on for BLASTER17 (388 k against 379 k at 8,192, 421 k against 384 k at 16,384) and from
+        //    4,096 instances on for QUAD12 (704 k against 620 k; at 3,072 the latency variant leads 616 k to 586 k).
+        h->throughput_batch = cfg->throughput_batch > 0 ? cfg->throughput_batch : (1 << 30);
+        h->qp8_batch = cfg->qp8_batch > 0 ? cfg->qp8_batch : (cfg->variant == 17 ? 8192 : 4096);
     }
     const size_t B = (size_t)h->max_batch;
     const size_t nX = B * (h->N + 1) * h->nx, nU = B * h->N * h->nu;

@@ -67,6 +67,7 @@ struct QpSmem {
     T Lcol[L::NZ * L::NUP];  // first NU columns of the L_k being factorised, row-major [NZ][NUP]
     T Linv[L::NUP];      // 1/diag(Luu)
     T cPi[L::NXP], cZx[L::NXP], cPv[L::NXP], cDx[L::NXP];  // carried: pi_{k+1}, dx-part of z_{k+1}, p_{k+1}, dx_k
+    T cDx2[L::NXP];      // forward sweeps: dx_k alternates between cDx and cDx2 (no sync between reading dx_k and writing dx_{k+1})
     T sT1[L::NXP], sT2[L::NXP], sDz[L::NZP], sRb[L::NXP];
     T hd[L::NZP], ds[L::NZP];  // Hd_k and sqrt(Hd_k) of every row, read by the pivot loop
 };
@@ -188,6 +189,27 @@ MPCB_DEV void apply_P(QpSmem<NX, NU, T, NSLOT> &sm, bool pform)
     warp_sync();
 }
 
+// acc + sum_c a[c] * b[c], c < N: four accumulator chains in the latency variant (one warp per scheduler: the chains are
+// the critical path), two in the register-capped throughput variant (measured: four cost it 1.6 % at 4,096 instances)
+template <int N, int CHAINS, typename T, class FA, class FB>
+MPCB_DEV T dot_chains(T acc, FA &&a, FB &&b)
+{
+    if constexpr (CHAINS == 4) {
+        T s0 = acc, s1 = T(0), s2 = T(0), s3 = T(0);
+        MPCB_UNROLL
+        for (int c = 0; c + 3 < N; c += 4) { s0 += a(c) * b(c); s1 += a(c + 1) * b(c + 1); s2 += a(c + 2) * b(c + 2); s3 += a(c + 3) * b(c + 3); }
+        MPCB_UNROLL
+        for (int c = N & ~3; c < N; c++) s0 += a(c) * b(c);
+        return (s0 + s1) + (s2 + s3);
+    } else {
+        T s0 = acc, s1 = T(0);
+        MPCB_UNROLL
+        for (int c = 0; c + 1 < N; c += 2) { s0 += a(c) * b(c); s1 += a(c + 1) * b(c + 1); }
+        if (N & 1) s0 += a(N - 1) * b(N - 1);
+        return s0 + s1;
+    }
+}
+
 // Forward substitution with the first NU columns of L_k held row-wise in registers:
 // on return lanes c < NU hold lvec_c = (Luu^{-1} l_u)_c and lanes NU.. hold l_x - Lxu lvec.
 template <int NU, typename T>
@@ -204,6 +226,36 @@ MPCB_DEV T fwd_subst(T l, const T *Lu, const T *invd, int nz)
     return out;
 }
 
+// The same substitution without the NU dependent shuffles: l_u goes through shared memory once (`bc`), Luu is read from
+// the column-major factor image `lu` (lu[c * NZP + r] = L[r][c], the record layout) and EVERY lane runs the NU-step
+// recurrence redundantly in registers -- same operations in the same order as fwd_subst, bit-identical results, but the
+// dependent chain is NU x (FMA + MUL) instead of NU x (shuffle + MUL + FMA) (a shuffle of a double is WARPSYNC + 2 SHFL).
+template <int NX, int NU, typename T>
+MPCB_DEV T fwd_subst_img(T l, const T *Lu, const T *invd, const T *lu, T *bc, int nz)
+{
+    using L = Layout<NX, NU>;
+    const int lane = lane_id();
+    if (lane < NU) bc[lane] = l;
+    warp_sync();
+    T lv[NU];
+    MPCB_UNROLL
+    for (int c = 0; c < NU; c++) {
+        T a = bc[c];
+        MPCB_UNROLL
+        for (int cc = 0; cc < c; cc++) a -= lu[cc * L::NZP + c] * lv[cc];
+        lv[c] = a * invd[c];
+    }
+    T out = l;
+    if (lane >= NU && lane < nz) {
+        MPCB_UNROLL
+        for (int c = 0; c < NU; c++) out -= Lu[c] * lv[c];
+    }
+    MPCB_UNROLL
+    for (int c = 0; c < NU; c++)
+        if (lane == c) out = lv[c];
+    return out;
+}
+
 // One forward sweep: dz_k = [du_k; dx_k] with du_k = -Luu^{-T}(lvec_k + Lxu' dx_k),
 // dx_{k+1} = r_k + [B A] dz_k.  FINAL additionally produces dpi_{k+1} = P_{k+1} dx_{k+1} + p_{k+1}.
 // The elementwise box work of the step just computed is folded in (it only depends on dz_k and
@@ -216,6 +268,8 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
     using L = Layout<NX, NU>;
     constexpr int NZ = L::NZ;
     constexpr int O_OUT = FINAL ? L::O_DZ : L::O_DZA;
+    // in-lane substitution: latency variant only (measured on the single-buffer throughput variant, 168-register cap: 1.2 % slower)
+    constexpr bool kInLane = (NSLOT == 2);
     const int lane = lane_id();
     const int N = P.N;
     // record k: [BAt | Lu | invd | lvec | rb | z tl tu ll lu lb ub]; FINAL: also [dza] and [Lxx | pv] of record k+1
@@ -238,6 +292,8 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
         T *wk = ws + (size_t)k * L::STAGE;
         const int half = (NSLOT == 2) ? (k & 1) : 0;
         const T *s = sm.slot[half];
+        const T *dxc = (k & 1) ? sm.cDx2 : sm.cDx;  // dx_k
+        T *dxn_ = (k & 1) ? sm.cDx : sm.cDx2;       // dx_{k+1}
         if (NSLOT == 2) {
             if (k + 1 < N) fetch(k + 1, (k + 1) & 1);
         } else {
@@ -259,26 +315,47 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
             const T *col = s + L::O_LU + lane * L::NZP + NU;
             MPCB_UNROLL
             for (int i = 0; i + 3 < NX; i += 4) {
-                a0 += col[i] * sm.cDx[i]; a1 += col[i + 1] * sm.cDx[i + 1];
-                a2 += col[i + 2] * sm.cDx[i + 2]; a3 += col[i + 3] * sm.cDx[i + 3];
+                a0 += col[i] * dxc[i]; a1 += col[i + 1] * dxc[i + 1];
+                a2 += col[i + 2] * dxc[i + 2]; a3 += col[i + 3] * dxc[i + 3];
             }
             MPCB_UNROLL
-            for (int i = NX & ~3; i < NX; i++) a0 += col[i] * sm.cDx[i];
+            for (int i = NX & ~3; i < NX; i++) a0 += col[i] * dxc[i];
             yy = -((a0 + a1) + (a2 + a3));
+            if (kInLane) sm.sT1[lane] = yy;
         }
-        T du = T(0);
-        MPCB_UNROLL
-        for (int i = NU - 1; i >= 0; i--) {
-            const T dui = warp_shfl(yy, i) * s[L::O_INVD + i];
-            if (lane == i) du = dui;
-            if (lane < i) yy -= s[L::O_LU + lane * L::NZP + i] * dui;
-        }
+        T duv[NU];
         T dz = T(0);
-        if (lane < NU) dz = du;
-        else if (lane < NZ) dz = sm.cDx[lane - NU];
-        if (lane < NZ) {
-            wk[O_OUT + lane] = dz;
-            sm.sDz[lane] = dz;
+        if constexpr (kInLane) {
+            warp_sync();
+            // back substitution du = Luu^{-T} yy, redundantly in every lane (yy through shared memory, Luu from the record
+            // image): NU x (FMA + MUL) on the dependent chain instead of NU x (shuffle + MUL + FMA); every lane ends up with
+            // all of du_k, so the product below takes it from registers and needs no broadcast of dz_k
+            MPCB_UNROLL
+            for (int i = NU - 1; i >= 0; i--) {
+                T a = sm.sT1[i];
+                MPCB_UNROLL
+                for (int c = NU - 1; c > i; c--) a -= s[L::O_LU + i * L::NZP + c] * duv[c];
+                duv[i] = a * s[L::O_INVD + i];
+            }
+            if (lane >= NU && lane < NZ) dz = dxc[lane - NU];
+            MPCB_UNROLL
+            for (int i = 0; i < NU; i++)
+                if (lane == i) dz = duv[i];
+            if (lane < NZ) wk[O_OUT + lane] = dz;
+        } else {
+            T du = T(0);
+            MPCB_UNROLL
+            for (int i = NU - 1; i >= 0; i--) {
+                const T dui = warp_shfl(yy, i) * s[L::O_INVD + i];
+                if (lane == i) du = dui;
+                if (lane < i) yy -= s[L::O_LU + lane * L::NZP + i] * dui;
+            }
+            if (lane < NU) dz = du;
+            else if (lane < NZ) dz = dxc[lane - NU];
+            if (lane < NZ) {
+                wk[O_OUT + lane] = dz;
+                sm.sDz[lane] = dz;
+            }
         }
         // box slacks / multipliers along this step (component `lane` of stage k)
         if (var_kind<NX, NU>(k, lane, N).hasb) {
@@ -302,21 +379,30 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
                 wk[L::O_C2 + lane] = itl - itu;
             }
         }
-        warp_sync();
-        // dx_{k+1} = rb_k + [B A] dz_k
+        // dx_{k+1} = rb_k + [B A] dz_k: du_k from this lane's registers (or the broadcast copy of dz_k), dx_k from the buffer read above
+        // (dx_{k+1} goes to the other one)
+        if (!kInLane) warp_sync();
         if (lane < NX) {
             T a0 = s[L::O_RB + lane], a1 = T(0), a2 = T(0), a3 = T(0);
-            MPCB_UNROLL
-            for (int j = 0; j + 3 < NZ; j += 4) {
-                a0 += s[L::O_BAT + j * L::LDB + lane] * sm.sDz[j];
-                a1 += s[L::O_BAT + (j + 1) * L::LDB + lane] * sm.sDz[j + 1];
-                a2 += s[L::O_BAT + (j + 2) * L::LDB + lane] * sm.sDz[j + 2];
-                a3 += s[L::O_BAT + (j + 3) * L::LDB + lane] * sm.sDz[j + 3];
-            }
-            MPCB_UNROLL
-            for (int j = NZ & ~3; j < NZ; j++) a0 += s[L::O_BAT + j * L::LDB + lane] * sm.sDz[j];
+            auto dzj = [&](auto J_) {
+                constexpr int j = decltype(J_)::value;
+                if constexpr (!kInLane) return sm.sDz[j];
+                else if constexpr (j < NU) return duv[j];
+                else return dxc[j - NU];
+            };
+            static_for<0, (NZ & ~3), 4>([&](auto J_) {
+                constexpr int j = decltype(J_)::value;
+                a0 += s[L::O_BAT + j * L::LDB + lane] * dzj(IntC<j>{});
+                a1 += s[L::O_BAT + (j + 1) * L::LDB + lane] * dzj(IntC<j + 1>{});
+                a2 += s[L::O_BAT + (j + 2) * L::LDB + lane] * dzj(IntC<j + 2>{});
+                a3 += s[L::O_BAT + (j + 3) * L::LDB + lane] * dzj(IntC<j + 3>{});
+            });
+            static_for<(NZ & ~3), NZ>([&](auto J_) {
+                constexpr int j = decltype(J_)::value;
+                a0 += s[L::O_BAT + j * L::LDB + lane] * dzj(IntC<j>{});
+            });
             const T dxn = (a0 + a1) + (a2 + a3);
-            sm.cDx[lane] = dxn;
+            dxn_[lane] = dxn;
             if (FINAL) {
                 // dpi_{k+1} = Lxx_{k+1} (Lxx_{k+1}' dx_{k+1}) + p_{k+1}
                 sm.sRb[lane] = dxn;
@@ -361,7 +447,7 @@ MPCB_DEV void forward_sweep(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, Stage
         }
     }
     // terminal stage: dz_N = [0; dx_N]
-    if (lane < NZ) ws[(size_t)N * L::STAGE + O_OUT + lane] = (lane < NU) ? T(0) : sm.cDx[lane - NU];
+    if (lane < NZ) ws[(size_t)N * L::STAGE + O_OUT + lane] = (lane < NU) ? T(0) : ((N & 1) ? sm.cDx2 : sm.cDx)[lane - NU];
     pipe_fence();
     warp_sync();
     imax_out = warp_max(imax);
@@ -623,11 +709,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 T ll = T(0), lu = T(0), tl = T(1), tu = T(1);
                 if (vk.hasb) { tl = s[L::O_TL + lane]; tu = s[L::O_TU + lane]; ll = s[L::O_LL + lane]; lu = s[L::O_LUP + lane]; }
                 if (vk.var) {
-                    T r0 = Hd * zj + s[L::O_G + lane] - ll + lu, r1 = T(0);
-                    MPCB_UNROLL
-                    for (int c = 0; c + 1 < NX; c += 2) { r0 += brow[c] * sm.cPi[c]; r1 += brow[c + 1] * sm.cPi[c + 1]; }
-                    if (NX & 1) r0 += brow[NX - 1] * sm.cPi[NX - 1];
-                    q = r0 + r1;
+                    q = dot_chains<NX, (NSLOT == 2 ? 4 : 2)>(Hd * zj + s[L::O_G + lane] - ll + lu, [&](int c) { return brow[c]; }, [&](int c) { return sm.cPi[c]; });
                     if (lane >= NU) q -= s[L::O_PI + lane - NU];
                     if (STRICT) xg = fmax(xg, fabs(q));
                 }
@@ -666,11 +748,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             // affine backward vector before the substitution: l = q + [B A]' t2 (the last use of this lane's row of [B A]')
             T lin;
             {
-                T l0 = q, l1 = T(0);
-                MPCB_UNROLL
-                for (int c = 0; c + 1 < NX; c += 2) { l0 += brow[c] * sm.sT2[c]; l1 += brow[c + 1] * sm.sT2[c + 1]; }
-                if (NX & 1) l0 += brow[NX - 1] * sm.sT2[NX - 1];
-                lin = l0 + l1;
+                lin = dot_chains<NX, (NSLOT == 2 ? 4 : 2)>(q, [&](int c) { return brow[c]; }, [&](int c) { return sm.sT2[c]; });
             }
             // W = [B A]' Lxx_{k+1}
             T w[NX];  // row `lane` of W (CUDA-core product, or read back from the tiles for the Householder loop)
@@ -955,7 +1033,18 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             MPCB_PH(3);
             MPCB_PH_COUNT(10);
             }
-            const T l = fwd_subst<NU, T>(lin, Lu, invd, NZ);
+            // the factor's input block goes to the (unfetched) Lu slice of the record image for the in-lane substitution
+            T l;
+            if constexpr (NSLOT == 2) {
+                T *luimg = sm.slot[half] + L::O_LU;
+                if (lane < NU) {
+                    MPCB_UNROLL
+                    for (int c = 0; c < NU; c++) luimg[c * L::NZP + lane] = Lu[c];
+                }
+                l = fwd_subst_img<NX, NU, T>(lin, Lu, invd, luimg, sm.sT1, NZ);
+            } else {
+                l = fwd_subst<NU, T>(lin, Lu, invd, NZ);
+            }
             if (lane < NU) wk[L::O_LVEC + lane] = l;
             else if (lane < NZ) { wk[L::O_PV + lane - NU] = l; sm.cPv[lane - NU] = l; }
             if (lane < NZ) {
@@ -1033,17 +1122,15 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 warp_sync();
                 const int jr = lane < NZ ? lane : 0;
                 const VarKind vk = var_kind<NX, NU>(k, lane, N);
-                T l0 = REFINE ? (lane < NZ ? s[L::O_C1 + jr] : T(0)) : (vk.hasb ? s[L::O_C1 + lane] - sigmu * s[L::O_C2 + lane] : T(0)), l1 = T(0);
-                MPCB_UNROLL
-                for (int c = 0; c + 1 < NX; c += 2) {
-                    l0 += s[L::O_BAT + jr * L::LDB + c] * sm.cPv[c];
-                    l1 += s[L::O_BAT + jr * L::LDB + c + 1] * sm.cPv[c + 1];
-                }
-                if (NX & 1) l0 += s[L::O_BAT + jr * L::LDB + NX - 1] * sm.cPv[NX - 1];
+                const T l0 = dot_chains<NX, (NSLOT == 2 ? 4 : 2)>(
+                    REFINE ? (lane < NZ ? s[L::O_C1 + jr] : T(0)) : (vk.hasb ? s[L::O_C1 + lane] - sigmu * s[L::O_C2 + lane] : T(0)),
+                    [&](int c) { return s[L::O_BAT + jr * L::LDB + c]; }, [&](int c) { return sm.cPv[c]; });
+                const T l1 = T(0);
                 T Lu[NU], invd[NU];
                 MPCB_UNROLL
                 for (int c = 0; c < NU; c++) { Lu[c] = s[L::O_LU + c * L::NZP + jr]; invd[c] = s[L::O_INVD + c]; }
-                const T l = fwd_subst<NU, T>((lane < NZ) ? l0 + l1 : T(0), Lu, invd, NZ);
+                const T l = (NSLOT == 2) ? fwd_subst_img<NX, NU, T>((lane < NZ) ? l0 + l1 : T(0), Lu, invd, s + L::O_LU, sm.sT1, NZ)
+                                         : fwd_subst<NU, T>((lane < NZ) ? l0 + l1 : T(0), Lu, invd, NZ);
                 warp_sync();
                 if (REFINE) {
                     // the increment stays separate ([d lvec; d p_k] replaces rho in the c1 slot): refine_forward adds the

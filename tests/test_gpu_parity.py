@@ -479,6 +479,33 @@ def test_poc_jacobian_generator(cuda_device):
     assert np.abs(U.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(X.cpu().numpy()[ok] - Xo[ok]).max() < TOL
 
 
+@pytest.mark.parametrize("variant,N,B", [(17, 20, 300), (12, 12, 77)])
+def test_single_buffer_variant_matches_c_oracle(cuda_device, variant, N, B):
+    """The single-buffer variant of the one-instance-per-warp kernel (no stage prefetch, Householder LQ on every iteration,
+    12 warps per SM).  No default chunk size selects it any more (the latency variant is faster at every size since it
+    carries P_k in its normal-equations iterations); mpcb_config.throughput_batch still forces it, so it stays checked:
+    two control steps against the C oracle and against the latency variant."""
+    P = bo.canonical_problem(N, variant)
+    x0, yref = sc.random_setpoints(B, seed=78, nx=P.nx, nu=P.nu)
+    trim = sc.hover_trim(P.nu)
+    mpct = _mpc(N, B, variant, throughput_batch=1, qp8_batch=1 << 30)
+    mpcl = _mpc(N, B, variant, throughput_batch=1 << 30, qp8_batch=1 << 30)
+    orc = co.BatchRTI(P, B)
+    for m in (mpct, mpcl, orc):
+        m.reset(x0, trim)
+    x = x0
+    for step in range(2):
+        ut, Xt, Ut, stt = mpct.solve(x, yref)
+        ul, Xl, Ul, stl = mpcl.solve(x, yref)
+        uo, Xo, Uo, sto = orc.solve(x, yref)
+        assert (stt.cpu().numpy() == sto).all() and (stl.cpu().numpy() == sto).all()
+        ok = sto == 0
+        assert ok.mean() > 0.95 and (mpct.iters.cpu().numpy()[ok] == orc.iters[ok]).all()
+        assert np.abs(Ut.cpu().numpy()[ok] - Uo[ok]).max() < TOL and np.abs(Xt.cpu().numpy()[ok] - Xo[ok]).max() < TOL
+        assert np.abs((Ut - Ul).cpu().numpy()[ok]).max() < TOL and np.abs((Xt - Xl).cpu().numpy()[ok]).max() < TOL
+        x = co.plant_step(P, x, uo)
+
+
 @pytest.mark.parametrize("variant,N,B", [(12, 20, 1024), (17, 20, 515), (12, 40, 130), (17, 7, 5)])
 def test_four_instances_per_warp_kernel_matches_c_oracle(cuda_device, variant, N, B):
     """The throughput variant of the QP kernel (mpcb_qp8.cuh: four instances per warp), forced for
@@ -559,7 +586,7 @@ def test_four_instances_per_warp_kernel_refill_with_infeasible_instances(cuda_de
 
 
 def test_quad12_default_scheduler_mixes_both_qp_kernels(cuda_device):
-    """QUAD12 with the default scheduler settings: chunks of >= 3,072 instances go to the
+    """QUAD12 with the default scheduler settings: chunks of >= 4,096 instances go to the
     four-instances-per-warp kernel, the remainder chunk to the one-instance kernel; a batch size that
     is no multiple of four leaves the last warp partly empty.  Every instance against the C oracle."""
     B, N = 9003, 8
