@@ -25,13 +25,17 @@
 namespace mpcb {
 
 // Complementarity above which the latency variant (NSLOT = 2) factorises the stage matrix in normal-equations form
-// (Gram matrix + Cholesky) instead of the Householder LQ; -DMPCB_GRAM_MU=1e30 switches it off (tools/ab.py).
-// Measured at 1,024 instances: -7.8 % launch time at 1e-4 (BLASTER17; QUAD12 -8.8 %), -10.2 % at 1e-6; the single-buffer
-// throughput variant (168-register cap, 12 warps per SM) spills with it and is 18 % slower, so it keeps the LQ throughout.
-// Also only while mu <= mu0: on an infeasible QP the multipliers diverge (mu climbs towards the 100 * mu0 exit) and the Gram
-// matrix loses a pivot before the LQ does -- the instance would end with ST_QPFAIL where the checkers report ST_MINSTEP.
+// (classical recursion on P_k: products on the FP64 tensor cores, NU pivots) instead of the Householder LQ;
+// -DMPCB_GRAM_MU=1e30 switches it off (tools/ab.py).  History of the switch, launch time at 1,024 instances: 1e-4 -7.8 %
+// (round 1, Gram + 23-pivot Cholesky), 1e-5 -1.3 % more (round 2); with the P form each interior-point iteration moved
+// from the LQ saves 20 x 6.7 k cycles, and 3e-6 gives -3.4 % more with every parity assertion of the GPU suite still
+// holding at a tolerance of 3e-7 (1e-7 except one 1.0e-7 < d < 3e-7 case; at 1e-5 all hold at 1e-7); 1e-6 fails three
+// tests with deviations up to 3.6e-6 (profiles/r02_ab_gram_mu.txt, r02_parity_margins.txt).  The single-buffer throughput
+// variant (168-register cap, 12 warps per SM) spills with it and is slower, so it keeps the LQ throughout.
+// Also only while mu <= mu0: on an infeasible QP the multipliers diverge (mu climbs towards the 100 * mu0 exit) and the
+// normal-equations form loses a pivot before the LQ does -- the instance would end with ST_QPFAIL where the checkers report ST_MINSTEP.
 #ifndef MPCB_GRAM_MU
-#define MPCB_GRAM_MU 1e-5
+#define MPCB_GRAM_MU 3e-6
 #endif
 // W = [B A]' Lxx and the Gram matrix W W' of the latency variant on the FP64 tensor cores (mma.sync m8n8k4, DMMA):
 // -DMPCB_DMMA=0 restores the CUDA-core products (tools/ab.py).
@@ -759,12 +763,12 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             constexpr int NI = (NZ + 7) / 8, NJ = (NX + 7) / 8, NS = (NX + 3) / 4;
             const int tg = lane >> 2, tq = lane & 3;
             T wt[NI][NJ][2];
+            T baf[2 * NJ][NI];  // P form: [B A]' fragments shared by the two products of the stage
             if constexpr (kDmma) {
                 static_for<0, NI>([&](auto I_) {
                     static_for<0, NJ>([&](auto J_) { wt[decltype(I_)::value][decltype(J_)::value][0] = T(0); wt[decltype(I_)::value][decltype(J_)::value][1] = T(0); });
                 });
-                auto wprod = [&](auto FULL_) {
-                    constexpr bool FULL = decltype(FULL_)::value != 0;  // P form: sm.Lxx is the full symmetric P_{k+1}, no tile is skipped
+                auto wprod = [&]() {  // factor form: W = [B A]' Lxx_{k+1}, Lxx lower triangular
                     static_for<0, NS>([&](auto S_) {
                         constexpr int st = decltype(S_)::value;
                         const int kk = 4 * st + tq;       // row of Lxx = column of [B A]' of this lane's fragments
@@ -779,7 +783,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                         });
                         static_for<0, NJ>([&](auto J_) {
                             constexpr int J = decltype(J_)::value;
-                            if constexpr (FULL || 8 * J <= 4 * st + 3) {  // some row of this k-step reaches the tile's columns (Lxx[j][c] = 0 for c > j)
+                            if constexpr (8 * J <= 4 * st + 3) {  // some row of this k-step reaches the tile's columns (Lxx[j][c] = 0 for c > j)
                                 const int col = 8 * J + tg;
                                 const bool in = kin && col < NX;
                                 const T v = sm.Lxx[in ? kk * NX + col : 0];
@@ -789,7 +793,37 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                         });
                     });
                 };
-                if (pform) wprod(IntC<1>{}); else wprod(IntC<0>{});
+                if (pform) {
+                    // P form: the k-steps run over (Jc, h) with k-index q <-> column 8 Jc + 2 q + h of [B A]' -- the assignment the
+                    // product M = T [B A] below needs for its B fragments, which are these A fragments: loaded once (baf)
+                    static_for<0, NJ>([&](auto C_) {
+                        constexpr int Jc = decltype(C_)::value;
+                        static_for<0, 2>([&](auto H_) {
+                            constexpr int h = decltype(H_)::value;
+                            if constexpr (8 * Jc + h < NX) {
+                                const int kk = 8 * Jc + 2 * tq + h;
+                                const bool kin = kk < NX;
+                                static_for<0, NI>([&](auto I_) {
+                                    constexpr int I = decltype(I_)::value;
+                                    const int row = 8 * I + tg;
+                                    const bool in = kin && row < NZ;
+                                    const T v = s[L::O_BAT + (in ? row * L::LDB + kk : 0)];
+                                    baf[2 * Jc + h][I] = in ? v : T(0);
+                                });
+                                static_for<0, NJ>([&](auto J_) {
+                                    constexpr int J = decltype(J_)::value;
+                                    const int col = 8 * J + tg;
+                                    const bool in = kin && col < NX;
+                                    const T v = sm.Lxx[in ? kk * NX + col : 0];
+                                    const T bf = in ? v : T(0);
+                                    static_for<0, NI>([&](auto I_) { constexpr int I = decltype(I_)::value; warp_dmma(wt[I][J][0], wt[I][J][1], baf[2 * Jc + h][I], bf); });
+                                });
+                            }
+                        });
+                    });
+                } else {
+                    wprod();
+                }
             } else {
                 MPCB_UNROLL
                 for (int c = 0; c < NX; c++) {
@@ -825,8 +859,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 if constexpr (kDmma) {
                     // M = T [B A] with T = [B A]' P_{k+1} in the accumulator registers (the product above).  The contraction runs
                     // over the columns of T, and ANY assignment of columns to k-indices is valid as long as A and B use the same
-                    // one: lane (g, q) feeds T[8 I + g][8 Jc + 2 q + h], which it holds, as A, and loads
-                    // [B A]'[8 J + g][8 Jc + 2 q + h] from the record image as B -- the k-steps run over (Jc, h).
+                    // one: lane (g, q) feeds T[8 I + g][8 Jc + 2 q + h], which it holds, as A, and [B A]'[8 J + g][8 Jc + 2 q + h]
+                    // as B -- the fragment it loaded as A for the product above (baf) -- the k-steps run over (Jc, h).
                     // NI (NI + 1) / 2 tiles x the k-steps that reach a column < NX (30 DMMAs, BLASTER17).
                     T mt[NI][NI][2];
                     static_for<0, NI>([&](auto I_) {
@@ -837,21 +871,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                         static_for<0, 2>([&](auto H_) {
                             constexpr int h = decltype(H_)::value;
                             if constexpr (8 * Jc + h < NX) {
-                                const int kk = 8 * Jc + 2 * tq + h;
-                                const bool kin = kk < NX;
-                                T bq[NI];
-                                static_for<0, NI>([&](auto J_) {
-                                    constexpr int J = decltype(J_)::value;
-                                    const int row = 8 * J + tg;
-                                    const bool in = kin && row < NZ;
-                                    const T v = s[L::O_BAT + (in ? row * L::LDB + kk : 0)];
-                                    bq[J] = in ? v : T(0);
-                                });
                                 static_for<0, NI>([&](auto I_) {
                                     constexpr int I = decltype(I_)::value;
                                     static_for<0, I + 1>([&](auto J_) {
                                         constexpr int J = decltype(J_)::value;
-                                        warp_dmma(mt[I][J][0], mt[I][J][1], wt[I][Jc][h], bq[J]);
+                                        warp_dmma(mt[I][J][0], mt[I][J][1], wt[I][Jc][h], baf[2 * Jc + h][J]);
                                     });
                                 });
                             }

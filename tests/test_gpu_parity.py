@@ -4,6 +4,8 @@ Tolerances (BASELINE.json north_star): FP64 |du|,|dx| <= 1e-6 at matched KKT tol
 Both sides run the same Mehrotra iteration with the same stopping test (HPIPM's default
 tolerances), so they are expected to agree to ~1e-9; the bound asserted is 1e-6.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -13,7 +15,7 @@ from oracle import blaster_oracle as bo
 from oracle import c_oracle as co
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-6  # FP64 parity bound of north_star
+TOL = float(os.environ.get("MPCB_TEST_TOL", "1e-6"))  # FP64 parity bound of north_star (the override is for margin measurements only: tools/ab.py runs)
 
 
 def _mpc(N, B, variant=17, **kw):
