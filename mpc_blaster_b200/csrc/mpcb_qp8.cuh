@@ -186,6 +186,38 @@ MPCB_DEV void g8_matvec_rows(const double *M, int ld, const double *x, int n, co
     for (int t = 0; t < NT_; t++) acc[t] += a1[t];
 }
 
+// Forward substitution of the lane's row slots with the NU factor columns of the stage (record image in shared memory):
+// l_u goes through the group's scratch once and EVERY lane runs the NU-step recurrence redundantly in registers -- the same
+// operations in the same order as a chain of NU group broadcasts (bit-identical), without the NU dependent shuffles
+// (WARPSYNC + 2 SHFL each, and a reconvergence before every one of them).
+template <int NX, int NU, int NT_>
+MPCB_DEV void g8_fwd_subst(Qp8Group<NX, NU> &sm, double (&l)[NT_], int s)
+{
+    using L = Layout<NX, NU>;
+    static_assert(NU <= kLPI, "the input rows must sit in the first row slot");
+    if (s < NU) sm.sT1[s] = l[0];
+    warp_sync();
+    double lv[NU];
+    MPCB_UNROLL
+    for (int c = 0; c < NU; c++) {
+        double a = sm.sT1[c];
+        MPCB_UNROLL
+        for (int cc = 0; cc < c; cc++) a -= sm.rec[L::O_LU + cc * L::NZP + c] * lv[cc];
+        lv[c] = a * sm.rec[L::O_INVD + c];
+    }
+    MPCB_UNROLL
+    for (int t = 0; t < NT_; t++) {
+        const int row = s + kLPI * t;
+        if (row >= NU && row < L::NZ) {
+            MPCB_UNROLL
+            for (int c = 0; c < NU; c++) l[t] -= sm.rec[L::O_LU + c * L::NZP + row] * lv[c];
+        }
+    }
+    MPCB_UNROLL
+    for (int c = 0; c < NU; c++)
+        if (s == c) l[0] = lv[c];
+}
+
 // Forward sweep (affine: FINAL = false, full step: FINAL = true), see forward_sweep in mpcb_qp.cuh.
 template <int NX, int NU, bool FINAL>
 MPCB_DEV void qp8_forward(const Params &P, Qp8Group<NX, NU> &sm, GrpPipe &pipe, double *__restrict__ ws, bool run, double sigmu,
@@ -246,12 +278,22 @@ MPCB_DEV void qp8_forward(const Params &P, Qp8Group<NX, NU> &sm, GrpPipe &pipe, 
             if (NX & 1) a0 += col[NX - 1] * sm.cDx[NX - 1];
             yy = -(a0 + a1);
         }
+        // back substitution du = Luu^{-T} yy, redundantly in every lane of the group (see g8_fwd_subst)
+        if (s < NU) sm.sT1[s] = yy;
+        warp_sync();
         double du = 0.0;
-        MPCB_UNROLL
-        for (int i = NU - 1; i >= 0; i--) {
-            const double dui = grp_bcast(yy, i) * sm.rec[L::O_INVD + i];
-            if (s == i) du = dui;
-            if (s < i) yy -= sm.rec[L::O_LU + s * L::NZP + i] * dui;
+        {
+            double duv[NU];
+            MPCB_UNROLL
+            for (int i = NU - 1; i >= 0; i--) {
+                double a = sm.sT1[i];
+                MPCB_UNROLL
+                for (int c = NU - 1; c > i; c--) a -= sm.rec[L::O_LU + i * L::NZP + c] * duv[c];
+                duv[i] = a * sm.rec[L::O_INVD + i];
+            }
+            MPCB_UNROLL
+            for (int i = 0; i < NU; i++)
+                if (s == i) du = duv[i];
         }
         MPCB_UNROLL
         for (int t = 0; t < NT; t++) {
@@ -740,17 +782,8 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
             }
             last_sig = sig;
             warp_sync();
-            // forward substitution with the u-columns of L
-            MPCB_UNROLL
-            for (int c = 0; c < NU; c++) {
-                const double lc = grp_bcast(l[0], c) * sm.rec[L::O_INVD + c];
-                if (s == c) l[0] = lc;
-                MPCB_UNROLL
-                for (int t = 0; t < NT; t++) {
-                    const int row = s + kLPI * t;
-                    if (row > c && row < NZ) l[t] -= sm.rec[L::O_LU + c * L::NZP + row] * lc;
-                }
-            }
+            // forward substitution with the u-columns of L (the pivot-row buffer is dead: its first half is the scratch)
+            g8_fwd_subst<NX, NU, NT>(sm, l, s);
             MPCB_UNROLL
             for (int t = 0; t < NT; t++) {
                 const int row = s + kLPI * t;
@@ -821,17 +854,7 @@ MPCB_DEV void qp8_solve_queue(const Params &P, Qp8Smem<NX, NU> &smw, const Qp8Ba
                     if (NX & 1) l0 += sm.rec[L::O_BAT + rr * L::LDB + NX - 1] * sm.cPv[NX - 1];
                     l[t] = (row < NZ) ? l0 + l1 : 0.0;
                 }
-                MPCB_UNROLL
-                for (int c = 0; c < NU; c++) {
-                    const double lc = grp_bcast(l[0], c) * sm.rec[L::O_INVD + c];
-                    if (s == c) l[0] = lc;
-                    MPCB_UNROLL
-                    for (int t = 0; t < NT; t++) {
-                        const int row = s + kLPI * t;
-                        if (row > c && row < NZ) l[t] -= sm.rec[L::O_LU + c * L::NZP + row] * lc;
-                    }
-                }
-                warp_sync();  // every lane has read cPv
+                g8_fwd_subst<NX, NU, NT>(sm, l, s);  // its warp_sync also orders every lane's reads of cPv above before the writes below
                 MPCB_UNROLL
                 for (int t = 0; t < NT; t++) {
                     const int row = s + kLPI * t;
