@@ -1232,6 +1232,8 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
         // ================= F4b: take the step
         {
             T cmax = T(0), msum = T(0);
+            // (ascending: the pass ends on the records the backward sweep S1 of the next iteration starts with; running it
+            // last-batch-first, so that it starts on what S4 touched last, measured 1.6 % slower at 1,024 instances)
             for (int k0 = 0; k0 <= N; k0 += FB) {
                 BoxIn<T, FB> in;
                 load_box<NX, NU, T, FB, true>(in, ws, k0, N + 1, N, lane);
