@@ -42,6 +42,10 @@ namespace mpcb {
 #ifndef MPCB_DMMA
 #define MPCB_DMMA 1
 #endif
+// NX = 8 n + 1 (BLASTER17): last column of P_{k+1} on the CUDA cores instead of a mostly empty third tile; -DMPCB_TAIL_COLUMN=0: all on the tensor cores
+#ifndef MPCB_TAIL_COLUMN
+#define MPCB_TAIL_COLUMN 1
+#endif
 #if defined(MPCB_PHASE_CLOCKS) && !defined(MPCB_HOST_EMU)
 // experiment build only (tools/phase_clocks.py): cycles per phase of the one-instance kernel, summed over warps
 __device__ unsigned long long g_phase_clk[16];
@@ -754,6 +758,13 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             {
                 lin = dot_chains<NX, (NSLOT == 2 ? 4 : 2)>(q, [&](int c) { return brow[c]; }, [&](int c) { return sm.sT2[c]; });
             }
+            // P form, NX = 8 n + 1 (BLASTER17): the last column of P_{k+1} would cost a third column tile and a fifth k-step
+            // of mostly padding on the tensor cores (27 of 75 DMMAs); it is taken on the CUDA cores instead -- T[:, NX-1]
+            // here, row per lane, while this lane's row of [B A]' is still in registers
+            constexpr bool kTail = (NSLOT == 2) && (MPCB_DMMA != 0) && (NX % 8 == 1) && (MPCB_TAIL_COLUMN != 0);
+            T t_tail = T(0);
+            if (kTail && pform)
+                t_tail = dot_chains<NX, 4>(T(0), [&](int c) { return brow[c]; }, [&](int c) { return sm.Lxx[(NX - 1) * NX + c]; });
             // W = [B A]' Lxx_{k+1}
             T w[NX];  // row `lane` of W (CUDA-core product, or read back from the tiles for the Householder loop)
             // Tensor-core form: W as NI x NJ tiles of 8 x 8, accumulated over NS k-steps of 4 rows of Lxx (lower triangular:
@@ -764,6 +775,7 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
             const int tg = lane >> 2, tq = lane & 3;
             T wt[NI][NJ][2];
             T baf[2 * NJ][NI];  // P form: [B A]' fragments shared by the two products of the stage
+            constexpr int NXT = kTail ? NX - 1 : NX, NJT = (NXT + 7) / 8;  // columns / column tiles the P-form products take on the tensor cores
             if constexpr (kDmma) {
                 static_for<0, NI>([&](auto I_) {
                     static_for<0, NJ>([&](auto J_) { wt[decltype(I_)::value][decltype(J_)::value][0] = T(0); wt[decltype(I_)::value][decltype(J_)::value][1] = T(0); });
@@ -796,13 +808,13 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                 if (pform) {
                     // P form: the k-steps run over (Jc, h) with k-index q <-> column 8 Jc + 2 q + h of [B A]' -- the assignment the
                     // product M = T [B A] below needs for its B fragments, which are these A fragments: loaded once (baf)
-                    static_for<0, NJ>([&](auto C_) {
+                    static_for<0, NJT>([&](auto C_) {
                         constexpr int Jc = decltype(C_)::value;
                         static_for<0, 2>([&](auto H_) {
                             constexpr int h = decltype(H_)::value;
-                            if constexpr (8 * Jc + h < NX) {
+                            if constexpr (8 * Jc + h < NXT) {
                                 const int kk = 8 * Jc + 2 * tq + h;
-                                const bool kin = kk < NX;
+                                const bool kin = kk < NXT;
                                 static_for<0, NI>([&](auto I_) {
                                     constexpr int I = decltype(I_)::value;
                                     const int row = 8 * I + tg;
@@ -810,10 +822,10 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                                     const T v = s[L::O_BAT + (in ? row * L::LDB + kk : 0)];
                                     baf[2 * Jc + h][I] = in ? v : T(0);
                                 });
-                                static_for<0, NJ>([&](auto J_) {
+                                static_for<0, NJT>([&](auto J_) {
                                     constexpr int J = decltype(J_)::value;
                                     const int col = 8 * J + tg;
-                                    const bool in = kin && col < NX;
+                                    const bool in = kin && col < NXT;
                                     const T v = sm.Lxx[in ? kk * NX + col : 0];
                                     const T bf = in ? v : T(0);
                                     static_for<0, NI>([&](auto I_) { constexpr int I = decltype(I_)::value; warp_dmma(wt[I][J][0], wt[I][J][1], baf[2 * Jc + h][I], bf); });
@@ -821,6 +833,19 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                             }
                         });
                     });
+                    if constexpr (kTail) {
+                        // row NX-1 of P_{k+1} (the k-index the tiles left out) into the tiles: T[i][c] += [B A]'[i][NX-1] P[NX-1][c]
+                        static_for<0, NI>([&](auto I_) {
+                            constexpr int I = decltype(I_)::value;
+                            const int row = 8 * I + tg;
+                            const T a = (row < NZ) ? s[L::O_BAT + (row < NZ ? row : 0) * L::LDB + NX - 1] : T(0);
+                            static_for<0, NJT>([&](auto J_) {
+                                constexpr int J = decltype(J_)::value;
+                                wt[I][J][0] += a * sm.Lxx[(NX - 1) * NX + 8 * J + 2 * tq];
+                                wt[I][J][1] += a * sm.Lxx[(NX - 1) * NX + 8 * J + 2 * tq + 1];
+                            });
+                        });
+                    }
                 } else {
                     wprod();
                 }
@@ -866,11 +891,11 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                     static_for<0, NI>([&](auto I_) {
                         static_for<0, NI>([&](auto J_) { mt[decltype(I_)::value][decltype(J_)::value][0] = T(0); mt[decltype(I_)::value][decltype(J_)::value][1] = T(0); });
                     });
-                    static_for<0, NJ>([&](auto C_) {
+                    static_for<0, NJT>([&](auto C_) {
                         constexpr int Jc = decltype(C_)::value;
                         static_for<0, 2>([&](auto H_) {
                             constexpr int h = decltype(H_)::value;
-                            if constexpr (8 * Jc + h < NX) {
+                            if constexpr (8 * Jc + h < NXT) {
                                 static_for<0, NI>([&](auto I_) {
                                     constexpr int I = decltype(I_)::value;
                                     static_for<0, I + 1>([&](auto J_) {
@@ -907,6 +932,13 @@ MPCB_DEV int qp_solve_warp(const Params &P, QpSmem<NX, NU, T, NSLOT> &sm, T *__r
                         static_for<0, NZ, 2>([&](auto Cc) {
                             constexpr int c = decltype(Cc)::value;
                             sp_ld2<c>(mrow, m[c], m[c + 1]);
+                        });
+                    }
+                    if constexpr (kTail) {
+                        // the column the tiles left out: M[i][c] += T[i][NX-1] [B A]'[c][NX-1], row per lane
+                        static_for<0, NZ>([&](auto Cc) {
+                            constexpr int c = decltype(Cc)::value;
+                            m[c] += t_tail * s[L::O_BAT + c * L::LDB + NX - 1];
                         });
                     }
                 } else {
