@@ -180,23 +180,26 @@ np.savez(sys.argv[3], **out)
 
 
 def test_hybrid_factorisation_agrees_with_householder_only_build(tmp_path):
-    """qp_kernel factorises in normal-equations form (Gram + Cholesky) while mu > MPCB_GRAM_MU = 1e-5 and by the
-    Householder LQ afterwards (mpcb_qp.cuh).  The same kernel source built with -DMPCB_GRAM_MU=1e30 (LQ on every
-    iteration) must take the same number of iterations and land on the same iterate; always-Gram (-DMPCB_GRAM_MU=-1)
-    is what this guards against: it changes iteration counts and moves u by up to 8e-6."""
+    """qp_kernel factorises in normal-equations form (the classical recursion on P_k, products on the emulated tensor-core
+    fragments, input pivots only) while mu > MPCB_GRAM_MU = 3e-6 and by the Householder LQ afterwards (mpcb_qp.cuh).  The
+    same kernel source built with -DMPCB_GRAM_MU=1e30 (LQ on every iteration) must take the same number of iterations and
+    land on the same iterate; always-Gram (-DMPCB_GRAM_MU=-1) is what this guards against: it changes iteration counts and
+    moves u by up to 8e-6.  Two more builds pin the pieces of the P form against each other: the
+    17th column of P on the tensor-core tiles as well (-DMPCB_TAIL_COLUMN=0), and the round-1 factor form of the
+    normal-equations iterations (-DMPCB_DMMA=0: CUDA-core Gram matrix, 23-pivot Cholesky, factor carried)."""
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     script = tmp_path / "case.py"
     script.write_text(_HYBRID_CASE)
     res = {}
-    for tag, defs in (("hybrid", ""), ("lq", "MPCB_GRAM_MU=1e30")):
+    for tag, defs in (("hybrid", ""), ("lq", "MPCB_GRAM_MU=1e30"), ("notail", "MPCB_TAIL_COLUMN=0"), ("factor", "MPCB_DMMA=0")):
         out = tmp_path / f"{tag}.npz"
         env = dict(os.environ, MPCB_EMU_DEFINES=defs)
         subprocess.check_call([sys.executable, str(script), os.path.dirname(here), os.path.join(here, "emu"), str(out)], env=env)
         res[tag] = np.load(out)
     assert sorted(res["hybrid"].files) == sorted(res["lq"].files) and len(res["lq"].files) == 6
-    for k, tag in ((k, tag) for k in res["lq"].files for tag in ("hybrid",)):
+    for k, tag in ((k, tag) for k in res["lq"].files for tag in ("hybrid", "notail", "factor")):
         a, b = res[tag][k], res["lq"][k]
         assert a[0] == b[0] == 0 and a[1] == b[1], (k, tag)    # status, IPM iterations
         # measured: hybrid 2e-12 (CUDA-core products), 6e-11 (tensor-core products: another summation order); Gram on every iteration 1e-9 on these cases and 8e-6 on cold random set-points
