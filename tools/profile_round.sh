@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'linearize_kernel|qp_kernel' -s 8 -c 2 -f \
     -o gpurun_out/${TAG}_full python bench.py --steps 6 --warmup 3 --no-cpu --no-large --no-quad12 > gpurun_out/${TAG}_ncu_full.log 2>&1
 [ "$2" = bench ] && { ls -la gpurun_out; exit 0; }   # `sh tools/profile_round.sh <tag> bench`: only the bench step's kernels
-# large batches: the one-instance throughput variant (forced: chunks of this size default to qp8_kernel), then qp8_kernel on both
+# large batches: the one-instance kernel (forced: chunks of this size default to qp8_kernel), then qp8_kernel on both
 # models.  gpurun brings back at most 64 MiB: of these captures only the raw-page CSV and the per-line profile travel.
 LIB=mpc_blaster_b200/lib/libmpcb.so
 cap() {  # cap <name> <kernel regex> <skip> <count> <sweep args...>
@@ -23,7 +23,8 @@ cap() {  # cap <name> <kernel regex> <skip> <count> <sweep args...>
     ncu -i gpurun_out/${TAG}_$NAME.ncu-rep --page raw --csv > gpurun_out/${TAG}_${NAME}_raw.csv
 }
 cap qp1_blaster17_16k 'linearize_kernel|qp_kernel' 2 2 --points "16384,20,17,rand" --qp8-batch 1000000000
-python tools/ncu_lines.py gpurun_out/${TAG}_qp1_blaster17_16k.ncu-rep $LIB qp_kernelILi17ELi6ELi1ELi1ELi12ELb0 > gpurun_out/${TAG}_qp1_throughput_kernel_lines.txt 2>&1 || true
+# (since the end of round 2 that is the latency variant: no default chunk size selects the single-buffer variant any more)
+python tools/ncu_lines.py gpurun_out/${TAG}_qp1_blaster17_16k.ncu-rep $LIB qp_kernelILi17ELi6ELi1ELi2ELi1ELb0 > gpurun_out/${TAG}_qp1_latency_16k_kernel_lines.txt 2>&1 || true
 rm -f gpurun_out/${TAG}_qp1_blaster17_16k.ncu-rep
 cap qp8_blaster17_16k 'qp8_kernel' 1 1 --points "16384,20,17,rand"
 python tools/ncu_lines.py gpurun_out/${TAG}_qp8_blaster17_16k.ncu-rep $LIB qp8_kernelILi17ELi6 > gpurun_out/${TAG}_qp8_kernel_lines.txt 2>&1 || true
